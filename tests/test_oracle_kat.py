@@ -1,0 +1,290 @@
+"""Known-answer tests that pin the CPU oracle.
+
+The reference ships no usable golden vectors for this path (main_test.go does not compile at the
+reference snapshot); these hand-derived KATs plus the 4-row toy dataset of main_test.go:107-112 are
+the oracle's only anchor ("parity unpinned").
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tests.util import toy_fixture, synth_dataset
+
+
+def make_oracle(**kw):
+    X, y, nrow = toy_fixture()
+    cfg = ob.make_config(population_size=kw.pop("population_size", 4), **kw)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    return o
+
+
+def test_philox_kat():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    assert ob.philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert ob.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert ob.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_rng_derivations():
+    r = ob.Rng(ob.RNG_PHILOX, 7)
+    r.seek(1, 2, 0)
+    a = [r.uint64() for _ in range(4)]
+    w = ob.philox([0, 1, 2, 0], [7, 0]) + ob.philox([1, 1, 2, 0], [7, 0])
+    assert a == [w[0] | w[1] << 32, w[2] | w[3] << 32, w[4] | w[5] << 32, w[6] | w[7] << 32]
+    # Float64 = float64(Int63)/2^63, Intn(power of two) = Int31 & (n-1)  (Go math/rand v1)
+    r.seek(1, 2, 0)
+    assert r.float64() == float(a[0] & (2**63 - 1)) / 2.0**63
+    assert r.intn(8) == ((a[1] & (2**63 - 1)) >> 32) & 7
+    # Intn(non power of two): rejection above max, then modulo
+    v = (a[2] & (2**63 - 1)) >> 32
+    mx = (1 << 31) - 1 - (1 << 31) % 100
+    assert v <= mx
+    assert r.intn(100) == v % 100
+    for kind in (ob.RNG_ALFG, ob.RNG_PHILOX):
+        r = ob.Rng(kind, 1)
+        xs = [r.intn(13) for _ in range(2000)]
+        assert min(xs) == 0 and max(xs) == 12
+        fs = [r.float64() for _ in range(2000)]
+        assert 0.0 <= min(fs) and max(fs) < 1.0 and 0.45 < sum(fs) / len(fs) < 0.55
+
+
+def test_alfg_is_seed_deterministic():
+    a, b, c = ob.Rng(ob.RNG_ALFG, 1), ob.Rng(ob.RNG_ALFG, 1), ob.Rng(ob.RNG_ALFG, 2)
+    sa = [a.uint64() for _ in range(700)]
+    assert sa == [b.uint64() for _ in range(700)]
+    assert sa != [c.uint64() for _ in range(700)]
+
+
+def test_tree_encoding_and_semantics():
+    o = make_oracle()
+    # (+ x0 (* x1 x0)) -> [0,3,4, 4, 2,7,8, 5, 4]; ids 0 + 1 - 2 * 3 / 4 x0 5 x1
+    t = np.array([0, 3, 4, 4, 2, 7, 8, 5, 4], np.int32)
+    sem = o.semantic_evaluate_array(t)
+    X, y, _ = toy_fixture()
+    np.testing.assert_array_equal(sem, X[:, 0] + X[:, 1] * X[:, 0])
+    assert sem[0] == 1.1 + 2.2 * 1.1 and sem[1] == 4.4 + 5.5 * 4.4
+    # x1 alone
+    np.testing.assert_array_equal(o.semantic_evaluate_array(np.array([5], np.int32)), X[:, 1])
+    # protected division: (/ x0 (- x1 x1)) -> all 1.0 ; (/ x0 x1) row0 = 0.5
+    np.testing.assert_array_equal(
+        o.semantic_evaluate_array(np.array([3, 3, 4, 4, 1, 7, 8, 5, 5], np.int32)), np.ones(4))
+    assert o.semantic_evaluate_array(np.array([3, 3, 4, 4, 5], np.int32))[0] == 1.1 / 2.2
+    # negative zero denominator is also "== 0": (/ x0 (* (- x0 x0) (- 0 ... ))) via -0.0 constant
+    o2 = make_oracle(num_random_constants=1, min_random_constant=-0.0, max_random_constant=-0.0)
+    assert o2.symbol_values()[6] == 0.0
+    assert o2.semantic_evaluate_array(np.array([3, 3, 4, 4, 6], np.int32))[0] == 1.0
+
+
+def test_exp64_and_sigmoid_quirks(oracle_lib):
+    L = oracle_lib
+    assert L.orc_exp64(0.0) == 1.0
+    assert L.orc_exp64(1e-17) == 0.0           # exp == 1 && v != 0 -> 0  (main_cpu.go:57-59)
+    assert L.orc_exp64(-1e-17) == 0.0
+    assert L.orc_exp64(710.0) == 1.7976931348623157e308   # +Inf -> MaxFloat64 (:53-55)
+    assert L.orc_exp64(float("inf")) == 1.7976931348623157e308
+    assert L.orc_exp64(float("-inf")) == 0.0
+    assert math.isnan(L.orc_exp64(float("nan")))
+    assert L.orc_exp64(1.0) == math.exp(1.0)
+    assert L.orc_sigmoid(0.0) == 0.5
+    assert L.orc_sigmoid(1e-17) == 1.0
+    assert L.orc_sigmoid(-1e-17) == 1.0
+    assert L.orc_sigmoid(-800.0) == 1.0 / 1.7976931348623157e308   # subnormal, not 0
+    assert L.orc_sigmoid(-800.0) > 0.0
+    assert L.orc_sigmoid(800.0) == 1.0
+    # boundary of the quirk: 1 + v == 1 exactly when v <= 2^-53 (ties-to-even) / v >= -2^-54
+    assert L.orc_exp64(2.0**-53) == 0.0 and L.orc_exp64(2.0**-52) == 1.0 + 2.0**-52
+    assert L.orc_exp64(-(2.0**-54)) == 0.0 and L.orc_exp64(-(2.0**-53)) == 1.0 - 2.0**-53
+
+
+def test_gs_operators_kat():
+    rng = np.random.default_rng(0)
+    p1, p2 = rng.normal(size=64), rng.normal(size=64)
+    np.testing.assert_array_equal(ob.gs_crossover(p1, p2, np.zeros(64)), 0.5 * p1 + 0.5 * p2)
+    r = rng.normal(size=64)
+    np.testing.assert_array_equal(ob.gs_mutation(p1, r, r, 0.73), p1)
+    s = 1.0 / (1.0 + np.exp(-r))
+    np.testing.assert_allclose(ob.gs_crossover(p1, p2, r), p1 * s + p2 * (1 - s), rtol=1e-15)
+    r2 = rng.normal(size=64)
+    s2 = 1.0 / (1.0 + np.exp(-r2))
+    np.testing.assert_allclose(ob.gs_mutation(p1, r, r2, 0.25), p1 + 0.25 * (s - s2), rtol=1e-14, atol=1e-16)
+
+
+@pytest.mark.parametrize("measure,expect", [(ob.MSE, 1.0), (ob.RMSE, 1.0), (ob.MAE, 1.0)])
+def test_fitness_kat(measure, expect):
+    o = make_oracle(error_measure=measure)
+    X, y, nrow = toy_fixture()
+    assert o.fitness_train(y[:nrow]) == 0.0 and o.fitness_test(y[nrow:]) == 0.0
+    assert o.fitness_train(y[:nrow] + 1) == pytest.approx(expect, rel=1e-15)
+    assert o.fitness_test(y[nrow:] + 1) == pytest.approx(expect, rel=1e-15)
+
+
+def test_fitness_mre_and_empty_test_set():
+    o = make_oracle(error_measure=ob.MRE)
+    X, y, nrow = toy_fixture()
+    assert o.fitness_train(y[:nrow] * 2) == pytest.approx(1.0, rel=1e-15)   # |y-2y|/y = 1
+    X2, y2, _ = synth_dataset(1, 8, 5)
+    cfg = ob.make_config(population_size=2)
+    o2 = ob.Oracle(cfg, X2, y2, 8)      # nrow_test == 0 -> 0/0 = NaN (Appendix A.13)
+    o2.create_T_F()
+    assert math.isnan(o2.fitness_test(np.zeros(0)))
+
+
+def test_workers_blocked_summation_order():
+    X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
+    sem = np.random.default_rng(1).normal(size=1000)
+    vals = []
+    for w in (1, 3, 8):
+        o = ob.Oracle(ob.make_config(population_size=2, n_workers=w), X, y, nrow)
+        o.create_T_F()
+        vals.append(o.fitness_train(sem))
+        block = (1000 + w - 1) // w
+        d = 0.0
+        parts = []
+        for k in range(w):
+            acc = 0.0
+            for i in range(block * k, min(block * (k + 1), 1000)):
+                acc += (y[i] - sem[i]) * (y[i] - sem[i])
+            parts.append(acc)
+        d = parts[0]
+        for pz in parts[1:]:
+            d += pz
+        assert vals[-1] == d / 1000.0
+        o.close()
+    assert max(vals) - min(vals) < 1e-12 * abs(vals[0])
+
+
+def test_tournament_kat():
+    o = make_oracle(population_size=8, tournament_size=1, rng_kind=ob.RNG_PHILOX, rng_seed=5)
+    r = ob.Rng(ob.RNG_PHILOX, 5)
+    o.L.orc_rng_seek(o.rng(), 3, 4, 0)
+    r.seek(3, 4, 0)
+    assert o.tournament_selection() == r.intn(8)       # size 1: returns its single draw
+    # all-equal fitness: returns the first draw; NaN first is never replaced; NaN later never wins
+    o = make_oracle(population_size=8, tournament_size=4, rng_kind=ob.RNG_PHILOX, rng_seed=5)
+    fit = np.ctypeslib.as_array(o.L.orc_fit(o.h), (8,))
+    for trial in range(50):
+        o.L.orc_rng_seek(o.rng(), 9, trial, 0)
+        r.seek(9, trial, 0)
+        draws = [r.intn(8) for _ in range(4)]
+        fit[:] = 1.0
+        assert o.tournament_selection() == draws[0]
+        o.L.orc_rng_seek(o.rng(), 9, trial, 0)
+        fit[:] = np.arange(8, dtype=float)
+        fit[draws[0]] = np.nan
+        assert o.tournament_selection() == draws[0]
+        o.L.orc_rng_seek(o.rng(), 9, trial, 0)
+        fit[:] = np.arange(8, dtype=float)
+        if draws[1] != draws[0]:
+            fit[draws[1]] = np.nan
+        exp = draws[0]
+        for d in draws[1:]:
+            if fit[d] < fit[exp]:
+                exp = d
+        assert o.tournament_selection() == exp
+
+
+def test_grow_tree_arrays_shape_and_draw_order():
+    X, y, nrow = synth_dataset(1, 20, 5)
+    for d in (1, 3, 6, 8):
+        o = ob.Oracle(ob.make_config(population_size=2, max_depth_creation=d, rng_kind=ob.RNG_PHILOX, rng_seed=11), X, y, nrow)
+        o.create_T_F()
+        for trial in range(200):
+            o.L.orc_rng_seek(o.rng(), 1, trial, 0)
+            t = o.create_grow_tree_arrays()
+            assert t[0] < 4, "root is a function unless zero_depth (main_cpu.go:610)"
+            assert len(t) <= 4 * 2**d - 3
+
+            # replay the draws by hand: Appendix A.7
+            r = ob.Rng(ob.RNG_PHILOX, 11)
+            r.seek(1, trial, 0)
+            out = []
+
+            def rec(depth):
+                if depth == 0:
+                    isf = True
+                elif depth == d:
+                    isf = False
+                else:
+                    isf = r.intn(2) != 0
+                if not isf:
+                    out.append(4 + r.intn(5))
+                    return
+                pos = len(out)
+                out.extend([r.intn(4), 0, 0])
+                for c in (1, 2):
+                    out[pos + c] = len(out)
+                    rec(depth + 1)
+            rec(0)
+            assert list(t) == out
+
+            def depth_of(i):
+                return 0 if t[i] >= 4 else 1 + max(depth_of(t[i + 1]), depth_of(t[i + 2]))
+            assert depth_of(0) <= d
+        o.close()
+
+
+def test_ramped_population_counts():
+    X, y, nrow = synth_dataset(1, 20, 5)
+    o = ob.Oracle(ob.make_config(population_size=100, max_depth_creation=6), X, y, nrow)
+    o.create_T_F()
+    o.initialize_population(0)
+    # sub_pop = 16, r = 4: depth 6 -> 10 full + 10 grow; depths 5..1 -> 8 full + 8 grow (:513-537)
+    def depth_of(t, i=0):
+        return 0 if t[i] >= 4 else 1 + max(depth_of(t, t[i + 1]), depth_of(t, t[i + 2]))
+    def n_nodes(t, i=0):
+        return 1 if t[i] >= 4 else 1 + n_nodes(t, t[i + 1]) + n_nodes(t, t[i + 2])
+    idx = 0
+    for j, n in zip(range(6, 0, -1), [20, 16, 16, 16, 16, 16]):
+        for k in range(n):
+            t = o.initial_tree(idx)
+            if k < (n + 1) // 2:
+                assert n_nodes(t) == 2 ** (j + 1) - 1 and depth_of(t) == j   # full tree
+            else:
+                assert depth_of(t) <= j and t[0] < 4
+            idx += 1
+    assert idx == 100
+
+
+def test_elite_is_preserved_and_draws_once():
+    X, y, nrow = synth_dataset(1, 125, 5, nrow=100)
+    o = ob.Oracle(ob.make_config(population_size=20, p_crossover=1.0, p_mutation=0.0, rng_seed=3), X, y, nrow)
+    o.create_T_F(); o.initialize_population(0); o.evaluate()
+    for g in range(5):
+        b = o.index_best
+        sem_b, fit_b = o.semantic(b), o.fit()[b]
+        o.generation()
+        plan = o.last_plan()
+        assert plan["elite"][b] == 1 and plan["p1"][b] == b and plan["tree0_off"][b] == -1
+        np.testing.assert_array_equal(o.semantic(b), sem_b)
+        assert o.fit()[b] == fit_b
+        assert o.fit()[o.index_best] <= fit_b
+
+
+def test_replay_equals_direct():
+    X, y, nrow = synth_dataset(1, 125, 5, nrow=100)
+    mk = lambda: ob.Oracle(ob.make_config(population_size=30, rng_seed=4, error_measure=ob.RMSE), X, y, nrow)
+    a, b = mk(), mk()
+    for o in (a, b):
+        o.create_T_F(); o.initialize_population(0); o.evaluate()
+    for g in range(6):
+        a.generation()
+        b.generation_replay(a.last_plan(), a.last_tree_pool())
+        np.testing.assert_array_equal(a.fit(), b.fit())
+        np.testing.assert_array_equal(a.semantics(), b.semantics())
+        assert a.index_best == b.index_best
+
+
+def test_format_float_go_v():
+    f = ob.format_float
+    assert f(0.5) == "0.5" and f(1.0) == "1" and f(100.0) == "100" and f(-2.25) == "-2.25"
+    assert f(0.1) == "0.1" and f(1 / 3) == "0.3333333333333333"
+    assert f(123456.0) == "123456" and f(1e6) == "1e+06" and f(1e21) == "1e+21"
+    assert f(0.0001) == "0.0001" and f(0.00001) == "1e-05"
+    assert f(1.7976931348623157e308) == "1.7976931348623157e+308"
+    assert f(5e-324) == "5e-324"
+    assert f(float("nan")) == "NaN" and f(float("inf")) == "+Inf" and f(float("-inf")) == "-Inf"
+    assert f(123456789.125) == "1.23456789125e+08"
