@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- individual-case semantic updates/s of the go-gsgp generation loop on B200.
+
+A "step" is one generation: one pass of the hot path (random-tree evaluation -> GS crossover /
+mutation / reproduction on the train+test semantics -> per-individual fitness -> selection) over
+the whole population.  One update = one fp64 element child[individual][case] produced.
+
+  value   device-RNG mode, everything resident in HBM (selection and random trees drawn on the
+          device): K generations timed with CUDA events on the library's stream, max over ranks.
+  e2e     host-replay mode through the reference-facing C-ABI call gsgp_generation() with HOST
+          buffers: every step the host builds the plan (tournaments on the previous generation's
+          fitness, random trees), the call uploads plan + programs, runs, and reads the fitness back.
+  roofline  the GS-operator+fitness kernel: algorithmic bytes (32 B per crossover/mutation update,
+          16 B per copied update) / CUDA-event time of its launches, against MEASURED_PEAKS.json.
+  cpu_baseline  the C oracle (a restatement of main_cpu.go, NOT go-gsgp itself) on the host cores.
+
+N>1: fitness cases are sharded; each rank holds `cases-per-gpu` cases of every individual (weak
+scaling), the only exchange is the 2*pop partial-sum all-gather (NCCL) per generation.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: 20 vars x 100k cases, pop 1000, crossover+mutation, 1 B200
+    "cfg2": dict(cfg_id=2, nvar=20, cases_per_gpu=100_000, pop=1000, depth=6, p_xo=0.6, p_mut=0.3,
+                 desc="synthetic 20 vars x 100k cases (80k train/20k test) per GPU, pop 1000, depth 6, p_xo 0.6 p_mut 0.3"),
+    # BASELINE.json configs[0]: the CPU-runnable case (latency-bound on a GPU)
+    "cfg1": dict(cfg_id=1, nvar=5, cases_per_gpu=1250, pop=100, depth=6, p_xo=0.6, p_mut=0.3,
+                 desc="synthetic 5 vars x 1000/250 cases, pop 100"),
+    # BASELINE.json configs[3]: deep trees, tree-eval bound (pop reduced to fit the default run time)
+    "cfg4": dict(cfg_id=4, nvar=20, cases_per_gpu=1_000_000, pop=5000, depth=8, p_xo=0.0, p_mut=1.0,
+                 desc="synthetic 20 vars x 1M cases per GPU, pop 5000, depth 8, p_mut 1.0"),
+    # BASELINE.json configs[4] per-GPU share at 8 GPUs with a population that fits one GPU
+    "cfg5": dict(cfg_id=5, nvar=20, cases_per_gpu=1_250_000, pop=1000, depth=6, p_xo=0.6, p_mut=0.3,
+                 desc="synthetic 20 vars x 1.25M cases per GPU (10M at 8 GPUs), pop 1000"),
+}
+
+
+def synth(cfg_id, n, v):
+    rng = np.random.Generator(np.random.PCG64(20261019 + cfg_id))
+    X = rng.uniform(-1.0, 1.0, size=(n, v))
+    y = X[:, 0] * X[:, 1] + 0.5 * X[:, 2] - X[:, 3] + 0.25 * X[:, 4] ** 2 + rng.normal(0.0, 0.01, size=n)
+    return X, y
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_arm(w, n_cases, pop, gens, warm, workers):
+    """Times the C restatement of main_cpu.go (the oracle) on the host cores: `gens` generations
+    at the full case count with a population of `pop`.  Returns updates/s and seconds."""
+    from oracle import binding as ob
+    X, y = synth(w["cfg_id"], n_cases, w["nvar"])
+    nrow = int(0.8 * n_cases)
+    cfg = ob.make_config(population_size=pop, rng_kind=ob.RNG_ALFG, rng_seed=1, error_measure=ob.RMSE,
+                         max_depth_creation=w["depth"], p_crossover=w["p_xo"], p_mutation=w["p_mut"],
+                         n_workers=workers)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F(); o.initialize_population(0); o.evaluate()
+    for _ in range(warm):
+        o.generation()
+    t0 = time.perf_counter()
+    for _ in range(gens):
+        o.generation()
+    dt = time.perf_counter() - t0
+    o.close()
+    return pop * n_cases * gens / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  go-gsgp cannot be built here
+    (no Go toolchain), so this is the oracle port of main_cpu.go with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    workers = os.cpu_count() or 1
+    n_cases = w["cases_per_gpu"]
+    pop = max(8, min(w["pop"], int(2e7 // n_cases)))           # bounded sample: ~2e7 updates per step
+    from oracle import binding as ob
+    ob.build()
+    value, dt = oracle_arm(w, n_cases, pop, args.steps, args.warmup, workers)
+    sample = f"{args.steps} generations at {n_cases} cases with a population subsample of {pop} (cost is linear in pop)"
+    line = {
+        "impl": "reference", "metric": "individual-case semantic updates/sec", "value": value, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}"},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": workers, "kind": "port", "sample": sample,
+                         "note": "C restatement of main_cpu.go (oracle); go-gsgp itself cannot be built (no Go toolchain)"},
+        "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-gens", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the gsgp_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from go_gsgp_b200 import Engine, capi, build
+    from go_gsgp_b200.host import HostDriver
+    build.build()
+
+    w = WORKLOADS[args.workload]
+    P, V = w["pop"], w["nvar"]
+    n_local = w["cases_per_gpu"]
+    n_global = n_local * world
+    nrow, nrow_test = int(0.8 * n_global), n_global - int(0.8 * n_global)
+    X, y = synth(w["cfg_id"], n_global, V)
+
+    nccl_id = None
+    if world > 1:
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    common = dict(population_size=P, nvar=V, nrow=nrow, nrow_test=nrow_test, max_depth_creation=w["depth"],
+                  error_measure=capi.RMSE, p_crossover=w["p_xo"], p_mutation=w["p_mut"], rng_seed=1,
+                  device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id)
+    host = HostDriver(population_size=P, nvar=V, max_depth_creation=w["depth"], p_crossover=w["p_xo"],
+                      p_mutation=w["p_mut"], seed=1)
+    sym = host.create_T_F()
+    init_trees = host.initialize_population(0)
+
+    def setup(rng_mode):
+        e = Engine(rng_mode=rng_mode, **common)
+        e.set_dataset(X, y)
+        e.set_constants(sym)
+        e.eval_initial(0, init_trees)
+        fit, fit_test, best = e.fitness_all()
+        return e, fit, best
+
+    K, W = args.steps, args.warmup
+    updates_per_step = float(P) * float(n_global)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- value: device-RNG mode, resident in HBM ------------------------------------------------
+    e, fit, best = setup(capi.RNG_DEVICE_PHILOX)
+    stream = torch.cuda.ExternalStream(e.stream)
+    e.run_generations(W)
+    e.sync()
+    launches0 = e.launch_count
+    e.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    e.run_generations(K)
+    ev1.record(stream)
+    e.sync()
+    barrier()
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
+    gpu_launches = e.launch_count - launches0
+    prof = {k: e.profile_read(k) for k in (capi.K_INTERP, capi.K_GSOP, capi.K_FINALIZE, capi.K_PLAN)}
+    e.profile_enable(False)
+    # exact algorithmic bytes of the GS launches need the op mix: count it from the last plan
+    plan = e.get_plan()
+    computed = (~plan["elite"].astype(bool)) & (plan["op"] != capi.OP_REPR)
+    frac_computed = float(np.mean(computed))
+    e.close()
+    value = updates_per_step * K / (ms_dev * 1e-3)
+
+    # ---- e2e: host-replay mode through gsgp_generation() with host buffers -------------------------
+    e, fit, best = setup(capi.RNG_HOST_REPLAY)
+    h2d = d2h = 0
+    def replay_step():
+        nonlocal fit, best, h2d, d2h
+        plan, pool = host.build_plan(fit, best)
+        fit, fit_test, best = e.generation(plan, pool)
+        # uploaded by the call: plan entries, postfix programs (one u16 per node; a tree of i ints
+        # has (i+1)/2 nodes), program offset/length tables
+        h2d = plan.nbytes + int((plan["tree0_len"] + 1)[plan["tree0_len"] > 0].sum()
+                                + (plan["tree1_len"] + 1)[plan["tree1_len"] > 0].sum()) + 16 * P
+        d2h = 16 * P + 4
+    for _ in range(W):
+        replay_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        replay_step()
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = updates_per_step * K / (ms_e2e * 1e-3)
+    e.close()
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant kernel (GS operators + fitness) ----------------------------------
+    peak, peak_src = measured_peak()
+    n_gs, ms_gs, _ = prof[capi.K_GSOP]
+    n_it, ms_it, _ = prof[capi.K_INTERP]
+    local_updates = float(P) * float(n_local)
+    gs_bytes_per_gen = local_updates * (32.0 * frac_computed + 16.0 * (1.0 - frac_computed))
+    gens_recorded = max(1, K)
+    achieved = gs_bytes_per_gen * gens_recorded / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
+    roofline = {"bound": "hbm", "kernel": "gsop_kernel (GS crossover/mutation/reproduction + error reduction)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_source": peak_src,
+                "bytes_per_update": 32.0 * frac_computed + 16.0 * (1.0 - frac_computed),
+                "launches": n_gs, "ms_total": ms_gs,
+                "interp_kernel": {"launches": n_it, "ms_total": ms_it},
+                "share_of_step": {"gsop": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        ob.build()
+        cores = os.cpu_count() or 1
+        pop_s = max(8, min(P, int(4e7 // n_local)))
+        v, dt = oracle_arm(w, n_local, pop_s, args.cpu_baseline_gens, 0, cores)
+        cpu_baseline = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_baseline_gens} generations at {n_local} cases, population subsample {pop_s} "
+                                  f"(cost linear in pop), {dt:.1f} s; C restatement of main_cpu.go, not go-gsgp"}
+
+    if rank == 0:
+        line = {
+            "metric": "individual-case semantic updates/sec", "value": value, "unit": "updates/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "global_cases": n_global, "pop": P,
+                       "l2": "inputs larger than L2 (semantic store %.2f GB per buffer per GPU)" % (P * n_local * 8 / 1e9),
+                       "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building"},
+            "gpu_launches": int(gpu_launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,849 @@
+// gsgp_b200.cu -- context + C-ABI (include/gsgp_b200.h) over the sm_100a kernels.
+//
+// The context owns: the dataset shard (variable-major X, targets y), the double-buffered semantic
+// store (init_tables main_cpu.go:1257-1284; update_tables :1191-1197 is a buffer flip), the fitness
+// tables, the generation plan + random trees + their postfix programs, the random-tree semantic
+// workspace R, the per-tile error partials, and one stream on which everything is issued in order.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: libnccl is dlopen()ed when world_size > 1
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "trees.hpp"
+
+using namespace gsgp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err)
+    {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString) {
+            err = "libnccl lacks a required symbol"; return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+template <typename T>
+struct PinnedBuf {                 // growable page-locked staging buffer
+    T *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)64);
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)64);
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct ProfSlot {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;   // recorded launches
+    size_t used = 0;
+    int64_t launches = 0;
+    double bytes = 0.0, ms = 0.0;
+};
+
+}  // namespace
+
+struct gsgp_ctx {
+    gsgp_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    Layout L{};
+    int32_t tr_lo = 0, tr_hi = 0, te_lo = 0, te_hi = 0;     // global row ranges of this shard
+    int32_t n_symbols = 0;
+    int32_t n_tiles = 0;
+    int32_t chunk_inds = 0;                                   // individuals per interp+gsop launch pair
+    int32_t tree_stride = 0, prog_stride = 0;
+    int32_t generation = 0;
+    int cur = 0;                                              // which store buffer holds generation g
+    bool have_dataset = false, fitness_valid = false;
+
+    double *dX = nullptr, *dy = nullptr, *dsym = nullptr;
+    double *dsem[2] = {nullptr, nullptr};
+    double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
+    double *dR = nullptr;
+    double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
+    gsgp_plan_entry *dplan = nullptr;
+    int32_t *dtree_pool = nullptr;                            // device mode
+    DevBuf<uint16_t> dprog_pool;
+    int32_t *dprog_off = nullptr, *dprog_len = nullptr, *dprog_maxsp = nullptr;
+    int32_t *dindex_best = nullptr;
+    BestRec *dhist = nullptr; int32_t hist_cap = 0;
+
+    PinnedBuf<gsgp_plan_entry> hplan;
+    PinnedBuf<uint16_t> hprog;
+    PinnedBuf<int32_t> hoff, hlen;
+    PinnedBuf<double> hfit;
+    PinnedBuf<int32_t> hint;
+    std::vector<int32_t> last_pool;                           // replay mode: last generation's trees
+    std::vector<gsgp_plan_entry> last_plan;
+    int32_t last_maxsp = 0;
+
+    ncclComm_t comm = nullptr;
+    ProfSlot prof[GSGP_K_COUNT];
+    bool profiling = false;
+    int64_t launch_count = 0;
+};
+
+namespace {
+
+int fail(gsgp_ctx *c, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CU(c, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail((c), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline int32_t round_up(int32_t x, int32_t m) { return (x + m - 1) / m * m; }
+
+struct ProfScope {                 // CUDA-event bracket around one kernel launch on ctx->stream
+    gsgp_ctx *c; int k; bool rec = false; size_t idx = 0;
+    ProfScope(gsgp_ctx *c_, int k_, double bytes) : c(c_), k(k_)
+    {
+        c->launch_count++;
+        ProfSlot &s = c->prof[k];
+        s.launches++;
+        if (!c->profiling) return;
+        if (s.used == s.ev.size()) {
+            if (s.ev.size() >= 16384) return;
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            s.ev.push_back({a, b});
+        }
+        idx = s.used++; rec = true; s.bytes += bytes;
+        cudaEventRecord(s.ev[idx].first, c->stream);
+    }
+    ~ProfScope() { if (rec) cudaEventRecord(c->prof[k].ev[idx].second, c->stream); }
+};
+
+// ---- launches ---------------------------------------------------------------------------------
+
+int launch_interp(gsgp_ctx *c, const uint16_t *prog_pool, const int32_t *prog_off, const int32_t *prog_len,
+                  int32_t first_slot, int32_t n_slots, int32_t max_sp, double *out, int64_t out_pitch,
+                  double n_trees_hint)
+{
+    if (n_slots <= 0) return 0;
+    InterpArgs a{};
+    a.prog_pool = prog_pool; a.prog_off = prog_off; a.prog_len = prog_len;
+    a.first_slot = first_slot; a.n_slots = n_slots;
+    a.X = c->dX; a.sym_val = c->dsym; a.nvar = c->cfg.nvar;
+    a.out = out; a.out_pitch = out_pitch; a.L = c->L;
+    dim3 grid((c->L.n_pad + kInterpTile - 1) / kInterpTile, (n_slots + kInterpWarps - 1) / kInterpWarps);
+    ProfScope ps(c, GSGP_K_INTERP, n_trees_hint * 8.0 * (double)(c->L.n_tr + c->L.n_te));
+    if (max_sp <= kRegStack) interp_kernel<kRegStack, false><<<grid, kInterpThreads, 0, c->stream>>>(a);
+    else if (max_sp <= kDeepStack) interp_kernel<1, true><<<grid, kInterpThreads, 0, c->stream>>>(a);
+    else return fail(c, "tree needs an operand stack of %d > %d", max_sp, kDeepStack);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, const double *sem_old,
+                double *sem_new, double bytes)
+{
+    if (nk <= 0) return 0;
+    GsArgs a{};
+    a.plan = c->dplan; a.sem_old = sem_old; a.sem_new = sem_new; a.R = c->dR; a.y = c->dy;
+    a.partial = c->dpartial; a.pitch = c->L.n_pad; a.k0 = k0; a.r_k0 = r_k0; a.n_tiles = c->n_tiles;
+    a.mode = mode; a.L = c->L;
+    dim3 grid(c->n_tiles, nk);
+    ProfScope ps(c, GSGP_K_GSOP, bytes);
+    switch (c->cfg.error_measure) {
+    case GSGP_MAE: gsop_kernel<GSGP_MAE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
+    case GSGP_MRE: gsop_kernel<GSGP_MRE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
+    default:       gsop_kernel<GSGP_MSE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
+    }
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+// local partials -> (all-gather across ranks) -> fitness -> best-of-generation
+int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf)
+{
+    const int P = c->cfg.population_size;
+    {
+        ReduceArgs r{c->dplan, c->dpartial, c->dsums, P, c->n_tiles, mode};
+        ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+        reduce_partials_kernel<<<(P * 32 + 255) / 256, 256, 0, c->stream>>>(r);
+        CU(c, cudaGetLastError());
+    }
+    const double *sums_all = c->dsums;
+    if (c->cfg.world_size > 1) {
+        ncclResult_t rc = g_nccl.AllGather(c->dsums, c->dsums_all, (size_t)2 * P, ncclDouble, c->comm, c->stream);
+        if (rc != ncclSuccess) return fail(c, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
+        sums_all = c->dsums_all;
+    }
+    {
+        FitnessArgs f{c->dplan, sums_all, c->dfit[old_buf], c->dfit_test[old_buf], c->dfit[new_buf],
+                      c->dfit_test[new_buf], P, c->cfg.world_size, mode, c->cfg.error_measure,
+                      c->cfg.nrow, c->cfg.nrow_test};
+        ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+        fitness_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(f);
+        CU(c, cudaGetLastError());
+    }
+    return 0;
+}
+
+int ensure_hist(gsgp_ctx *c, int32_t gen)
+{
+    if (gen < c->hist_cap) return 0;
+    int32_t cap = std::max(gen + 1, std::max(1024, c->hist_cap * 2));
+    BestRec *n = nullptr;
+    CU(c, cudaMalloc((void **)&n, sizeof(BestRec) * (size_t)cap));
+    CU(c, cudaMemsetAsync(n, 0, sizeof(BestRec) * (size_t)cap, c->stream));
+    if (c->dhist) {
+        CU(c, cudaMemcpyAsync(n, c->dhist, sizeof(BestRec) * (size_t)c->hist_cap, cudaMemcpyDeviceToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->dhist);
+    }
+    c->dhist = n; c->hist_cap = cap;
+    return 0;
+}
+
+int launch_best(gsgp_ctx *c, int buf, int32_t gen)
+{
+    if (ensure_hist(c, gen)) return 1;
+    ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+    best_kernel<<<1, 1024, 0, c->stream>>>(c->dfit[buf], c->dfit_test[buf], c->cfg.population_size,
+                                           c->cfg.minimization_problem, c->dindex_best, c->dhist + gen);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+// algorithmic bytes of the GS-operator launches: XO / MUT 32 B, copy 16 B per update
+double gs_bytes(const gsgp_plan_entry *plan, int32_t k0, int32_t nk, double n_cases)
+{
+    double b = 0.0;
+    for (int32_t k = k0; k < k0 + nk; ++k) {
+        const bool computed = !plan[k].elite && (plan[k].op == GSGP_OP_XO || plan[k].op == GSGP_OP_MUT);
+        b += (computed ? 32.0 : 16.0) * n_cases;
+    }
+    return b;
+}
+
+// the interp -> gsop pipeline of one generation, chunked so that R fits its workspace
+int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may be NULL */, int32_t max_sp)
+{
+    const int P = c->cfg.population_size;
+    const int old_buf = c->cur, new_buf = c->cur ^ 1;
+    const double n_cases = (double)(c->L.n_tr + c->L.n_te);
+    for (int32_t k0 = 0; k0 < P; k0 += c->chunk_inds) {
+        const int32_t nk = std::min(c->chunk_inds, P - k0);
+        double n_trees = 1.2 * nk, bytes = 30.4 * nk * n_cases;       // expected mix when the plan lives on the device
+        if (host_plan) {
+            n_trees = 0;
+            for (int32_t k = k0; k < k0 + nk; ++k) n_trees += (host_plan[k].tree0_len > 0) + (host_plan[k].tree1_len > 0);
+            bytes = gs_bytes(host_plan, k0, nk, n_cases);
+        }
+        if (launch_interp(c, c->dprog_pool.p, c->dprog_off, c->dprog_len, 2 * k0, 2 * nk, max_sp, c->dR,
+                          c->L.n_pad, n_trees)) return 1;
+        if (launch_gsop(c, GS_MODE_GENERATION, k0, nk, k0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
+    }
+    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf)) return 1;
+    c->cur = new_buf;                                                  // update_tables main_cpu.go:1191-1197
+    c->generation++;
+    if (launch_best(c, c->cur, c->generation)) return 1;               // :1492
+    c->fitness_valid = true;
+    return 0;
+}
+
+int launch_plan(gsgp_ctx *c, int32_t generation)
+{
+    PlanArgs a{};
+    a.plan = c->dplan; a.tree_pool = c->dtree_pool; a.prog_pool = c->dprog_pool.p;
+    a.prog_len = c->dprog_len; a.prog_maxsp = c->dprog_maxsp;
+    a.fit = c->dfit[c->cur]; a.index_best = c->dindex_best;
+    a.P = c->cfg.population_size; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
+    a.max_depth = c->cfg.max_depth_creation; a.zero_depth = c->cfg.zero_depth;
+    a.tournament_size = c->cfg.tournament_size; a.minimize = c->cfg.minimization_problem;
+    a.tree_stride = c->tree_stride; a.prog_stride = c->prog_stride;
+    a.generation = generation; a.p_xo = c->cfg.p_crossover; a.p_mut = c->cfg.p_mutation;
+    a.seed = c->cfg.rng_seed;
+    ProfScope ps(c, GSGP_K_PLAN, 0.0);
+    plan_kernel<<<(a.P + 127) / 128, 128, 0, c->stream>>>(a);
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+// host trees (reference array format) -> postfix programs in pinned staging; returns max stack need
+int stage_programs(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len, const int32_t *off,
+                   const int32_t *len, std::vector<uint16_t> &progs, int32_t *hoff, int32_t *hlen, int32_t &max_sp)
+{
+    progs.clear();
+    max_sp = 0;
+    std::string err;
+    for (int32_t t = 0; t < n; ++t) {
+        if (len[t] <= 0 || off[t] < 0) { hoff[t] = 0; hlen[t] = 0; continue; }
+        if ((int64_t)off[t] + len[t] > pool_len) return fail(c, "tree %d exceeds the tree pool", t);
+        const size_t start = progs.size();
+        int32_t sp = 0;
+        if (!prefix_to_postfix(pool + off[t], len[t], c->n_symbols, progs, sp, err))
+            return fail(c, "tree %d: %s", t, err.c_str());
+        hoff[t] = (int32_t)start; hlen[t] = (int32_t)(progs.size() - start);
+        max_sp = std::max(max_sp, sp);
+    }
+    return 0;
+}
+
+int check_ready(gsgp_ctx *c)
+{
+    if (!c) return fail(nullptr, "null context");
+    if (!c->have_dataset) return fail(c, "dataset not set (gsgp_set_dataset)");
+    CU(c, cudaSetDevice(c->cfg.device));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int32_t gsgp_abi_version(void) { return GSGP_ABI_VERSION; }
+
+void gsgp_config_defaults(gsgp_config *cfg)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->population_size = 200; cfg->max_depth_creation = 6; cfg->tournament_size = 4;
+    cfg->minimization_problem = 1; cfg->error_measure = GSGP_MSE;
+    cfg->p_crossover = 0.6; cfg->p_mutation = 0.3; cfg->rng_seed = 1;
+    cfg->rng_mode = GSGP_RNG_HOST_REPLAY; cfg->world_size = 1;
+}
+
+const char *gsgp_last_error(const gsgp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gsgp_nccl_unique_id(uint8_t out[128])
+{
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, "%s", err.c_str());
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclResult_t rc = g_nccl.GetUniqueId(&id);
+    if (rc != ncclSuccess) return fail(nullptr, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+    memcpy(out, &id, 128);
+    return 0;
+}
+
+void gsgp_shard_range(int32_t n, int32_t rank, int32_t world, int32_t *lo, int32_t *hi)
+{
+    *lo = (int32_t)((int64_t)n * rank / world);
+    *hi = (int32_t)((int64_t)n * (rank + 1) / world);
+}
+
+int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
+{
+    if (!cfg || !out) return fail(nullptr, "null argument");
+    *out = nullptr;
+    if (cfg->population_size < 1 || cfg->population_size > 65535 * 16)
+        return fail(nullptr, "population_size out of range");
+    if (cfg->nvar < 1 || cfg->nrow < 0 || cfg->nrow_test < 0 || cfg->nrow + (int64_t)cfg->nrow_test < 1)
+        return fail(nullptr, "bad dataset shape");
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(nullptr, "bad rank/world_size");
+    if (cfg->error_measure < GSGP_MSE || cfg->error_measure > GSGP_MRE) return fail(nullptr, "Unknown error measure");
+    if (cfg->tournament_size < 1) return fail(nullptr, "tournament_size must be >= 1");
+    if (cfg->p_crossover < 0 || cfg->p_mutation < 0 || cfg->p_crossover + cfg->p_mutation > 1)   // main_cpu.go:374-376
+        return fail(nullptr, "Crossover rate and mutation rate must be greater or equal to 0 and their sum must be smaller or equal to 1.");
+    if (4 + (int64_t)cfg->nvar + cfg->num_constants > 0xFFFF) return fail(nullptr, "too many symbols");
+    if (cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX && (cfg->max_depth_creation < 1 || cfg->max_depth_creation > kMaxGenDepth))
+        return fail(nullptr, "device RNG mode supports max_depth_creation in [1,%d]", kMaxGenDepth);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, "no CUDA device: the gsgp_b200 path has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "bad device ordinal %d", cfg->device);
+
+    gsgp_ctx *c = new gsgp_ctx();
+    c->cfg = *cfg;
+    auto bail = [&](void) { g_create_error = c->err; gsgp_destroy(c); return 1; };
+#define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fail(c, "%s failed: %s", #call, cudaGetErrorString(e__)); return bail(); } } while (0)
+    CUC(cudaSetDevice(cfg->device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    gsgp_shard_range(cfg->nrow, cfg->rank, cfg->world_size, &c->tr_lo, &c->tr_hi);
+    gsgp_shard_range(cfg->nrow_test, cfg->rank, cfg->world_size, &c->te_lo, &c->te_hi);
+    c->L.n_tr = c->tr_hi - c->tr_lo; c->L.n_te = c->te_hi - c->te_lo;
+    c->L.tr_pad = round_up(c->L.n_tr, 16);
+    c->L.n_pad = c->L.tr_pad + round_up(c->L.n_te, 16);
+    if (c->L.n_pad == 0) c->L.n_pad = 16;
+    c->n_tiles = (c->L.n_pad + kGsTile - 1) / kGsTile;
+    c->n_symbols = 4 + cfg->nvar + cfg->num_constants;
+
+    const int P = cfg->population_size;
+    const size_t row = (size_t)c->L.n_pad;
+    CUC(cudaMalloc((void **)&c->dX, sizeof(double) * row * cfg->nvar));
+    CUC(cudaMalloc((void **)&c->dy, sizeof(double) * row));
+    CUC(cudaMalloc((void **)&c->dsym, sizeof(double) * (size_t)c->n_symbols));
+    CUC(cudaMemsetAsync(c->dX, 0, sizeof(double) * row * cfg->nvar, c->stream));
+    CUC(cudaMemsetAsync(c->dy, 0, sizeof(double) * row, c->stream));
+    CUC(cudaMemsetAsync(c->dsym, 0, sizeof(double) * (size_t)c->n_symbols, c->stream));
+    for (int b = 0; b < 2; ++b) {
+        CUC(cudaMalloc((void **)&c->dsem[b], sizeof(double) * row * P));
+        CUC(cudaMemsetAsync(c->dsem[b], 0, sizeof(double) * row * P, c->stream));
+        CUC(cudaMalloc((void **)&c->dfit[b], sizeof(double) * P));
+        CUC(cudaMalloc((void **)&c->dfit_test[b], sizeof(double) * P));
+        CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * P, c->stream));
+        CUC(cudaMemsetAsync(c->dfit_test[b], 0, sizeof(double) * P, c->stream));
+    }
+    CUC(cudaMalloc((void **)&c->dpartial, sizeof(double) * 2 * (size_t)P * c->n_tiles));
+    CUC(cudaMalloc((void **)&c->dsums, sizeof(double) * 2 * P));
+    CUC(cudaMalloc((void **)&c->dsums_all, sizeof(double) * 2 * P * (size_t)cfg->world_size));
+    CUC(cudaMalloc((void **)&c->dplan, sizeof(gsgp_plan_entry) * P));
+    CUC(cudaMemsetAsync(c->dplan, 0, sizeof(gsgp_plan_entry) * P, c->stream));
+    CUC(cudaMalloc((void **)&c->dprog_off, sizeof(int32_t) * 2 * P));
+    CUC(cudaMalloc((void **)&c->dprog_len, sizeof(int32_t) * 2 * P));
+    CUC(cudaMalloc((void **)&c->dprog_maxsp, sizeof(int32_t) * 2 * P));
+    CUC(cudaMemsetAsync(c->dprog_len, 0, sizeof(int32_t) * 2 * P, c->stream));
+    CUC(cudaMalloc((void **)&c->dindex_best, sizeof(int32_t)));
+    CUC(cudaMemsetAsync(c->dindex_best, 0, sizeof(int32_t), c->stream));
+
+    if (cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX) {
+        const int d = cfg->max_depth_creation;
+        c->prog_stride = (1 << (d + 1));                       // nodes <= 2^(d+1)-1
+        c->tree_stride = 4 * (1 << d);                         // ints  <= 4*2^d-3 (main_cpu.go:609-639)
+        CUC(cudaMalloc((void **)&c->dtree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
+        CUC(c->dprog_pool.reserve((size_t)2 * P * c->prog_stride));
+        std::vector<int32_t> off(2 * (size_t)P);
+        for (int t = 0; t < 2 * P; ++t) off[t] = t * c->prog_stride;
+        CUC(cudaMemcpyAsync(c->dprog_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, c->stream));
+        CUC(cudaStreamSynchronize(c->stream));
+    }
+
+    // random-tree semantic workspace R: two rows per individual of a chunk
+    size_t free_b = 0, total_b = 0;
+    CUC(cudaMemGetInfo(&free_b, &total_b));
+    const size_t pair = 2 * row * sizeof(double);
+    size_t budget = cfg->workspace_bytes > 0 ? (size_t)cfg->workspace_bytes
+                                             : std::max<size_t>((size_t)1 << 30, free_b / 4);
+    if (cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) budget = pair * P;
+    size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)P, budget / pair));
+    chunk = std::min<size_t>(chunk, 65535);
+    if (chunk * pair > free_b) { fail(c, "not enough device memory for the tree-semantic workspace"); return bail(); }
+    c->chunk_inds = (int32_t)chunk;
+    CUC(cudaMalloc((void **)&c->dR, chunk * pair));
+    CUC(cudaMemsetAsync(c->dR, 0, chunk * pair, c->stream));
+
+    if (cfg->world_size > 1) {
+        std::string err;
+        if (!g_nccl.load(err)) { fail(c, "%s", err.c_str()); return bail(); }
+        ncclUniqueId id; memcpy(&id, cfg->nccl_id, 128);
+        ncclResult_t rc = g_nccl.CommInitRank(&c->comm, cfg->world_size, id, cfg->rank);
+        if (rc != ncclSuccess) { fail(c, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); return bail(); }
+    }
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = c;
+    return 0;
+}
+
+void gsgp_destroy(gsgp_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    for (auto &s : c->prof) for (auto &e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dsym);
+    for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
+    cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
+    cudaFree(c->dplan); cudaFree(c->dtree_pool); cudaFree(c->dprog_off); cudaFree(c->dprog_len);
+    cudaFree(c->dprog_maxsp); cudaFree(c->dindex_best); cudaFree(c->dhist);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gsgp_local_counts(const gsgp_ctx *c, int32_t *nrow_local, int32_t *nrow_test_local)
+{
+    if (!c) return 1;
+    if (nrow_local) *nrow_local = c->L.n_tr;
+    if (nrow_test_local) *nrow_test_local = c->L.n_te;
+    return 0;
+}
+
+int gsgp_set_dataset_shard(gsgp_ctx *c, const double *train_rows, const double *test_rows)
+{
+    if (!c) return fail(nullptr, "null context");
+    CU(c, cudaSetDevice(c->cfg.device));
+    const int V = c->cfg.nvar;
+    const int32_t n[2] = {c->L.n_tr, c->L.n_te};
+    const double *src[2] = {train_rows, test_rows};
+    const int32_t dst0[2] = {0, c->L.tr_pad};
+    for (int s = 0; s < 2; ++s) {
+        if (n[s] == 0) continue;
+        if (!src[s]) return fail(c, "null dataset pointer");
+        double *tmp = nullptr;
+        const size_t bytes = sizeof(double) * (size_t)n[s] * (V + 1);
+        CU(c, cudaMalloc((void **)&tmp, bytes));
+        CU(c, cudaMemcpyAsync(tmp, src[s], bytes, cudaMemcpyHostToDevice, c->stream));
+        transpose_dataset_kernel<<<(n[s] + 255) / 256, 256, 0, c->stream>>>(tmp, n[s], V, c->dX, c->dy, c->L.n_pad, dst0[s]);
+        c->launch_count++;
+        CU(c, cudaGetLastError());
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+    }
+    c->have_dataset = true;
+    return 0;
+}
+
+int gsgp_set_dataset(gsgp_ctx *c, const double *rowmajor)
+{
+    if (!c) return fail(nullptr, "null context");
+    if (!rowmajor) return fail(c, "null dataset pointer");
+    const size_t stride = (size_t)c->cfg.nvar + 1;
+    return gsgp_set_dataset_shard(c, rowmajor + (size_t)c->tr_lo * stride,
+                                  rowmajor + ((size_t)c->cfg.nrow + c->te_lo) * stride);
+}
+
+int gsgp_set_constants(gsgp_ctx *c, const double *sym_val, int32_t n_symbols)
+{
+    if (!c) return fail(nullptr, "null context");
+    if (n_symbols != c->n_symbols) return fail(c, "expected %d symbol values, got %d", c->n_symbols, n_symbols);
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaMemcpyAsync(c->dsym, sym_val, sizeof(double) * (size_t)n_symbols, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gsgp_seed_semantic(gsgp_ctx *c, int32_t ind, const double *sem)
+{
+    if (check_ready(c)) return 1;
+    if (ind < 0 || ind >= c->cfg.population_size) return fail(c, "individual %d out of range", ind);
+    double *row = c->dsem[c->cur] + (size_t)ind * c->L.n_pad;
+    if (c->L.n_tr)
+        CU(c, cudaMemcpyAsync(row, sem + c->tr_lo, sizeof(double) * (size_t)c->L.n_tr, cudaMemcpyHostToDevice, c->stream));
+    if (c->L.n_te)
+        CU(c, cudaMemcpyAsync(row + c->L.tr_pad, sem + c->cfg.nrow + c->te_lo, sizeof(double) * (size_t)c->L.n_te,
+                              cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->fitness_valid = false;
+    return 0;
+}
+
+static int eval_trees_into(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len, const int32_t *off,
+                           const int32_t *len, double *dout, int64_t pitch)
+{
+    std::vector<uint16_t> progs;
+    std::vector<int32_t> hoff(n), hlen(n);
+    int32_t max_sp = 0;
+    if (stage_programs(c, n, pool, pool_len, off, len, progs, hoff.data(), hlen.data(), max_sp)) return 1;
+    DevBuf<uint16_t> dp; DevBuf<int32_t> doff, dlen;
+    CU(c, dp.reserve(progs.size())); CU(c, doff.reserve(n)); CU(c, dlen.reserve(n));
+    CU(c, cudaMemcpyAsync(dp.p, progs.data(), sizeof(uint16_t) * progs.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(doff.p, hoff.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dlen.p, hlen.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    for (int32_t t0 = 0; t0 < n; t0 += 65535 * kInterpWarps) {
+        const int32_t nt = std::min<int32_t>(n - t0, 65535 * kInterpWarps);
+        if (launch_interp(c, dp.p, doff.p, dlen.p, t0, nt, max_sp, dout + (int64_t)t0 * pitch, pitch, nt)) return 1;
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gsgp_eval_initial(gsgp_ctx *c, int32_t first_ind, int32_t n, const int32_t *tree_pool, int32_t pool_len,
+                      const int32_t *tree_off, const int32_t *tree_len)
+{
+    if (check_ready(c)) return 1;
+    if (n < 0 || first_ind < 0 || first_ind + (int64_t)n > c->cfg.population_size) return fail(c, "individual range out of bounds");
+    if (n == 0) return 0;
+    for (int32_t t = 0; t < n; ++t) if (tree_len[t] <= 0) return fail(c, "individual %d has no tree", first_ind + t);
+    c->fitness_valid = false;
+    return eval_trees_into(c, n, tree_pool, pool_len, tree_off, tree_len,
+                           c->dsem[c->cur] + (size_t)first_ind * c->L.n_pad, c->L.n_pad);
+}
+
+int gsgp_eval_trees(gsgp_ctx *c, int32_t n, const int32_t *tree_pool, int32_t pool_len, const int32_t *tree_off,
+                    const int32_t *tree_len, double *out)
+{
+    if (check_ready(c)) return 1;
+    if (n <= 0) return 0;
+    DevBuf<double> tmp;
+    const size_t row = (size_t)c->L.n_pad;
+    const int32_t batch = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)1 << 30) / (row * 8)));
+    CU(c, tmp.reserve((size_t)batch * row));
+    const int32_t nl = c->L.n_tr + c->L.n_te;
+    for (int32_t t0 = 0; t0 < n; t0 += batch) {
+        const int32_t nt = std::min(batch, n - t0);
+        if (eval_trees_into(c, nt, tree_pool, pool_len, tree_off + t0, tree_len + t0, tmp.p, c->L.n_pad)) return 1;
+        if (c->L.n_tr)
+            CU(c, cudaMemcpy2DAsync(out + (size_t)t0 * nl, sizeof(double) * nl, tmp.p, sizeof(double) * row,
+                                    sizeof(double) * c->L.n_tr, nt, cudaMemcpyDeviceToHost, c->stream));
+        if (c->L.n_te)
+            CU(c, cudaMemcpy2DAsync(out + (size_t)t0 * nl + c->L.n_tr, sizeof(double) * nl, tmp.p + c->L.tr_pad,
+                                    sizeof(double) * row, sizeof(double) * c->L.n_te, nt, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+static int read_fitness(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_best)
+{
+    const int P = c->cfg.population_size;
+    CU(c, c->hfit.reserve(2 * (size_t)P)); CU(c, c->hint.reserve(4));
+    if (fit) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (fit_test) CU(c, cudaMemcpyAsync(c->hfit.p + P, c->dfit_test[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (index_best) CU(c, cudaMemcpyAsync(c->hint.p, c->dindex_best, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (fit) memcpy(fit, c->hfit.p, sizeof(double) * P);
+    if (fit_test) memcpy(fit_test, c->hfit.p + P, sizeof(double) * P);
+    if (index_best) *index_best = c->hint.p[0];
+    return 0;
+}
+
+int gsgp_fitness_all(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_best)
+{
+    if (check_ready(c)) return 1;
+    const int P = c->cfg.population_size;
+    const double n_cases = (double)(c->L.n_tr + c->L.n_te);
+    for (int32_t k0 = 0; k0 < P; k0 += 65535) {
+        const int32_t nk = std::min(65535, P - k0);
+        if (launch_gsop(c, GS_MODE_FITNESS_ONLY, k0, nk, 0, c->dsem[c->cur], c->dsem[c->cur], 8.0 * nk * n_cases)) return 1;
+    }
+    if (launch_finalize(c, GS_MODE_FITNESS_ONLY, c->cur, c->cur)) return 1;
+    if (launch_best(c, c->cur, c->generation)) return 1;
+    c->fitness_valid = true;
+    return read_fitness(c, fit, fit_test, index_best);
+}
+
+int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                    double *fit_out, double *fit_test_out, int32_t *index_best_out)
+{
+    if (check_ready(c)) return 1;
+    if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
+    if (!plan) return fail(c, "null plan");
+    const int P = c->cfg.population_size;
+    CU(c, c->hplan.reserve(P)); CU(c, c->hoff.reserve(2 * (size_t)P)); CU(c, c->hlen.reserve(2 * (size_t)P));
+    std::vector<int32_t> off(2 * (size_t)P), len(2 * (size_t)P);
+    for (int k = 0; k < P; ++k) {
+        const gsgp_plan_entry &e = plan[k];
+        if (e.op != GSGP_OP_XO && e.op != GSGP_OP_MUT && e.op != GSGP_OP_REPR) return fail(c, "plan[%d]: bad operator %d", k, e.op);
+        if (e.p1 < 0 || e.p1 >= P) return fail(c, "plan[%d]: parent index %d out of range", k, e.p1);
+        const bool computed = !e.elite && e.op != GSGP_OP_REPR;
+        if (computed && e.op == GSGP_OP_XO && (e.p2 < 0 || e.p2 >= P)) return fail(c, "plan[%d]: parent index %d out of range", k, e.p2);
+        const bool t0 = computed, t1 = computed && e.op == GSGP_OP_MUT;
+        if (t0 && e.tree0_len <= 0) return fail(c, "plan[%d]: missing random tree", k);
+        if (t1 && e.tree1_len <= 0) return fail(c, "plan[%d]: missing second random tree", k);
+        off[2 * k] = t0 ? e.tree0_off : -1; len[2 * k] = t0 ? e.tree0_len : 0;
+        off[2 * k + 1] = t1 ? e.tree1_off : -1; len[2 * k + 1] = t1 ? e.tree1_len : 0;
+        c->hplan.p[k] = e;
+    }
+    std::vector<uint16_t> progs;
+    int32_t max_sp = 0;
+    if (stage_programs(c, 2 * P, tree_pool, pool_len, off.data(), len.data(), progs, c->hoff.p, c->hlen.p, max_sp)) return 1;
+    CU(c, c->hprog.reserve(progs.size()));
+    memcpy(c->hprog.p, progs.data(), sizeof(uint16_t) * progs.size());
+    CU(c, c->dprog_pool.reserve(progs.size()));
+    CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->dprog_pool.p, c->hprog.p, sizeof(uint16_t) * progs.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->dprog_off, c->hoff.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->dprog_len, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
+    if (run_generation_kernels(c, c->hplan.p, max_sp)) return 1;
+    c->last_plan.assign(plan, plan + P);
+    c->last_pool.assign(tree_pool, tree_pool + std::max(pool_len, 0));
+    return read_fitness(c, fit_out, fit_test_out, index_best_out);
+}
+
+int gsgp_run_generations(gsgp_ctx *c, int32_t n)
+{
+    if (check_ready(c)) return 1;
+    if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_run_generations needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
+    if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
+    const int32_t max_sp = c->cfg.max_depth_creation + 1;
+    if (ensure_hist(c, c->generation + n)) return 1;
+    for (int32_t g = 0; g < n; ++g) {
+        if (launch_plan(c, c->generation + 1)) return 1;
+        if (run_generation_kernels(c, nullptr, max_sp)) return 1;
+    }
+    c->last_plan.clear();
+    return 0;
+}
+
+int gsgp_sync(gsgp_ctx *c)
+{
+    if (!c) return fail(nullptr, "null context");
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gsgp_get_fitness(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_best)
+{
+    if (check_ready(c)) return 1;
+    return read_fitness(c, fit, fit_test, index_best);
+}
+
+static int copy_row_out(gsgp_ctx *c, const double *row, double *out)
+{
+    if (c->L.n_tr) CU(c, cudaMemcpyAsync(out, row, sizeof(double) * (size_t)c->L.n_tr, cudaMemcpyDeviceToHost, c->stream));
+    if (c->L.n_te) CU(c, cudaMemcpyAsync(out + c->L.n_tr, row + c->L.tr_pad, sizeof(double) * (size_t)c->L.n_te, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gsgp_get_semantic(gsgp_ctx *c, int32_t ind, double *out)
+{
+    if (check_ready(c)) return 1;
+    if (ind < 0 || ind >= c->cfg.population_size) return fail(c, "individual %d out of range", ind);
+    return copy_row_out(c, c->dsem[c->cur] + (size_t)ind * c->L.n_pad, out);
+}
+
+int gsgp_get_tree_semantic(gsgp_ctx *c, int32_t ind, int32_t which, double *out)
+{
+    if (check_ready(c)) return 1;
+    if (!(c->cfg.flags & GSGP_FLAG_KEEP_TREE_SEMANTICS)) return fail(c, "context created without GSGP_FLAG_KEEP_TREE_SEMANTICS");
+    if (ind < 0 || ind >= c->cfg.population_size || which < 0 || which > 1) return fail(c, "bad tree selector");
+    return copy_row_out(c, c->dR + (size_t)(2 * ind + which) * c->L.n_pad, out);
+}
+
+int gsgp_get_plan(gsgp_ctx *c, gsgp_plan_entry *plan_out)
+{
+    if (check_ready(c)) return 1;
+    const int P = c->cfg.population_size;
+    if (!c->last_plan.empty()) { memcpy(plan_out, c->last_plan.data(), sizeof(gsgp_plan_entry) * P); return 0; }
+    CU(c, cudaMemcpyAsync(plan_out, c->dplan, sizeof(gsgp_plan_entry) * P, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gsgp_get_tree(gsgp_ctx *c, int32_t ind, int32_t which, int32_t *out, int32_t cap, int32_t *len)
+{
+    if (check_ready(c)) return 1;
+    if (ind < 0 || ind >= c->cfg.population_size || which < 0 || which > 1) return fail(c, "bad tree selector");
+    gsgp_plan_entry e;
+    if (!c->last_plan.empty()) e = c->last_plan[ind];
+    else {
+        CU(c, cudaMemcpyAsync(&e, c->dplan + ind, sizeof e, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    const int32_t off = which ? e.tree1_off : e.tree0_off, n = which ? e.tree1_len : e.tree0_len;
+    if (len) *len = n;
+    if (n <= 0) return 0;
+    if (n > cap) return fail(c, "tree buffer too small (%d > %d)", n, cap);
+    if (!c->last_plan.empty()) { memcpy(out, c->last_pool.data() + off, sizeof(int32_t) * n); return 0; }
+    CU(c, cudaMemcpyAsync(out, c->dtree_pool + off, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gsgp_get_history(gsgp_ctx *c, int32_t first, int32_t n, double *best_fit, double *best_fit_test, int32_t *best_index)
+{
+    if (check_ready(c)) return 1;
+    if (first < 0 || n < 0 || first + n > c->generation + 1 || first + n > c->hist_cap) return fail(c, "history range out of bounds");
+    std::vector<BestRec> h(n);
+    CU(c, cudaMemcpyAsync(h.data(), c->dhist + first, sizeof(BestRec) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) {
+        if (best_fit) best_fit[i] = h[i].fit;
+        if (best_fit_test) best_fit_test[i] = h[i].fit_test;
+        if (best_index) best_index[i] = h[i].index;
+    }
+    return 0;
+}
+
+int32_t gsgp_generation_index(const gsgp_ctx *c) { return c ? c->generation : -1; }
+
+int gsgp_set_fitness(gsgp_ctx *c, const double *fit, const double *fit_test)
+{
+    if (check_ready(c)) return 1;
+    const int P = c->cfg.population_size;
+    if (fit) CU(c, cudaMemcpyAsync(c->dfit[c->cur], fit, sizeof(double) * P, cudaMemcpyHostToDevice, c->stream));
+    if (fit_test) CU(c, cudaMemcpyAsync(c->dfit_test[c->cur], fit_test, sizeof(double) * P, cudaMemcpyHostToDevice, c->stream));
+    if (launch_best(c, c->cur, c->generation)) return 1;
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->fitness_valid = true;
+    return 0;
+}
+
+int gsgp_draw_plan(gsgp_ctx *c, int32_t generation, gsgp_plan_entry *plan_out)
+{
+    if (check_ready(c)) return 1;
+    if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_draw_plan needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
+    if (launch_plan(c, generation)) return 1;
+    c->last_plan.clear();
+    CU(c, cudaMemcpyAsync(plan_out, c->dplan, sizeof(gsgp_plan_entry) * c->cfg.population_size, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void *gsgp_stream(gsgp_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int gsgp_profile_enable(gsgp_ctx *c, int32_t on)
+{
+    if (!c) return 1;
+    c->profiling = on != 0;
+    if (on) for (auto &s : c->prof) { s.used = 0; s.launches = 0; s.bytes = 0.0; s.ms = 0.0; }
+    return 0;
+}
+
+int gsgp_profile_read(gsgp_ctx *c, int32_t kernel, int64_t *launches, double *total_ms, double *algorithmic_bytes)
+{
+    if (!c || kernel < 0 || kernel >= GSGP_K_COUNT) return 1;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    ProfSlot &s = c->prof[kernel];
+    double ms = 0.0;
+    for (size_t i = 0; i < s.used; ++i) {
+        float t = 0.f;
+        CU(c, cudaEventElapsedTime(&t, s.ev[i].first, s.ev[i].second));
+        ms += t;
+    }
+    if (launches) *launches = (int64_t)s.used;
+    if (total_ms) *total_ms = ms;
+    if (algorithmic_bytes) *algorithmic_bytes = s.bytes;
+    return 0;
+}
+
+int64_t gsgp_launch_count(const gsgp_ctx *c) { return c ? c->launch_count : 0; }
+
+}  // extern "C"

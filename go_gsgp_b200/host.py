@@ -1,0 +1,114 @@
+"""Binding of include/gsgp_host.h: the host-side driver pieces (RNG, constants, initial trees,
+per-generation plan) used by the Python harness and mirrored by the C++ CLI driver."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import PLAN_DTYPE
+
+
+class HostParams(C.Structure):
+    _fields_ = [
+        ("population_size", C.c_int32), ("nvar", C.c_int32), ("num_constants", C.c_int32),
+        ("max_depth_creation", C.c_int32), ("tournament_size", C.c_int32),
+        ("zero_depth", C.c_int32), ("minimization_problem", C.c_int32), ("init_type", C.c_int32),
+        ("p_crossover", C.c_double), ("p_mutation", C.c_double),
+        ("min_random_constant", C.c_double), ("max_random_constant", C.c_double),
+    ]
+
+
+HOST_SIGNATURES = {
+    "gsgph_rng_new": (C.c_void_p, [C.c_int64]),
+    "gsgph_rng_free": (None, [C.c_void_p]),
+    "gsgph_rng_float64": (C.c_double, [C.c_void_p]),
+    "gsgph_rng_intn": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "gsgph_create_T_F": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.POINTER(C.c_double)]),
+    "gsgph_initialize_population": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.POINTER(C.c_int32),
+                                              C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gsgph_build_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.POINTER(C.c_double), C.c_int32, C.c_void_p,
+                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "gsgph_best_individual": (C.c_int32, [C.POINTER(HostParams), C.POINTER(C.c_double)]),
+    "gsgph_format_float": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
+}
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = capi.load()
+    if not _bound:
+        for name, (res, args) in HOST_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _bound = True
+    return L
+
+
+def format_float(v: float) -> str:
+    buf = C.create_string_buffer(64)
+    _lib().gsgph_format_float(float(v), buf, 64)
+    return buf.value.decode()
+
+
+class HostDriver:
+    """The RNG-order-defining half of main_cpu.go's main(): seeds the RNG, draws the constants,
+    builds the initial population and, each generation, the plan the device applies."""
+
+    def __init__(self, *, population_size, nvar, num_constants=0, max_depth_creation=6, tournament_size=4,
+                 zero_depth=False, minimization_problem=True, init_type=2, p_crossover=0.6, p_mutation=0.3,
+                 min_random_constant=-100.0, max_random_constant=100.0, seed=1):
+        self.L = _lib()
+        self.p = HostParams(population_size, nvar, num_constants, max_depth_creation, tournament_size,
+                            int(zero_depth), int(minimization_problem), init_type, p_crossover, p_mutation,
+                            min_random_constant, max_random_constant)
+        self.rng = self.L.gsgph_rng_new(seed)                    # rand.Seed main_cpu.go:1367
+        self.P = population_size
+        d = max(max_depth_creation, 1)
+        self._tree_cap = 4 * (1 << d)
+        self._plan = np.zeros(self.P, PLAN_DTYPE)
+        self._pool = np.zeros(2 * self.P * self._tree_cap, np.int32)
+
+    def close(self):
+        if self.rng:
+            self.L.gsgph_rng_free(self.rng)
+            self.rng = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def create_T_F(self) -> np.ndarray:
+        sv = np.zeros(4 + self.p.nvar + self.p.num_constants)
+        self.L.gsgph_create_T_F(self.rng, C.byref(self.p), capi.dptr(sv))
+        return sv
+
+    def initialize_population(self, n_seeds=0):
+        n = self.P - n_seeds
+        cap = max(1, n) * (self._tree_cap + 4)
+        pool = np.zeros(cap, np.int32)
+        off, ln, used = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), C.c_int32()
+        rc = self.L.gsgph_initialize_population(self.rng, C.byref(self.p), n_seeds, capi.iptr(pool), cap,
+                                                capi.iptr(off), capi.iptr(ln), C.byref(used))
+        if rc:
+            raise RuntimeError(f"gsgph_initialize_population failed ({rc})")
+        return [pool[off[i]: off[i] + ln[i]].copy() for i in range(n)]
+
+    def build_plan(self, fit: np.ndarray, index_best: int):
+        """Returns (plan, pool) views valid until the next call."""
+        fit = np.ascontiguousarray(fit, np.float64)
+        used = C.c_int32()
+        rc = self.L.gsgph_build_plan(self.rng, C.byref(self.p), capi.dptr(fit), index_best, self._plan.ctypes.data,
+                                     capi.iptr(self._pool), len(self._pool), C.byref(used))
+        if rc:
+            raise RuntimeError("gsgph_build_plan: tree pool overflow")
+        return self._plan, self._pool[: max(used.value, 1)]
+
+    def best_individual(self, fit) -> int:
+        fit = np.ascontiguousarray(fit, np.float64)
+        return self.L.gsgph_best_individual(C.byref(self.p), capi.dptr(fit))

@@ -1,0 +1,59 @@
+/*
+ * gsgp_host.h -- host-side half of the hot path: the parts of main_cpu.go's driver that stay on the
+ * CPU (they define the RNG draw order) restated in C++ for hosts that cannot link Go: the seeded
+ * RNG, create_T_F's constants, the initial-population tree builders and the per-generation
+ * "plan" = the decisions of the sequential loop at main_cpu.go:1447-1470 without its arithmetic.
+ * A Go host (main_b200.go) keeps its own main_cpu.go code for all of this and only
+ * needs gsgp_b200.h; the C++ CLI driver and the Python harness use these entry points instead.
+ * Exported from the same libgsgp_b200.so.  No CUDA involved.
+ */
+#ifndef GSGP_HOST_H
+#define GSGP_HOST_H
+
+#include <stdint.h>
+#include "gsgp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsgph_rng gsgph_rng;
+
+/* math/rand stand-in: Go's additive lagged Fibonacci source (607,273) and Go's derivations of
+ * Float64/Intn.  Go's 607-entry seed table is not available offline, so the
+ * state is filled by splitmix64(seed): streams are reproducible, not equal to Go's. */
+gsgph_rng *gsgph_rng_new(int64_t seed);                    /* rand.Seed   main_cpu.go:1367 */
+void       gsgph_rng_free(gsgph_rng *r);
+double     gsgph_rng_float64(gsgph_rng *r);
+int32_t    gsgph_rng_intn(gsgph_rng *r, int32_t n);
+
+typedef struct {
+    int32_t population_size, nvar, num_constants;
+    int32_t max_depth_creation, tournament_size;
+    int32_t zero_depth, minimization_problem, init_type;   /* init_type: 0 grow, 1 full, 2 ramped */
+    double  p_crossover, p_mutation;
+    double  min_random_constant, max_random_constant;
+} gsgph_params;
+
+/* create_T_F (main_cpu.go:426-455): Symbol.value per id; draws one Float64 per constant */
+int gsgph_create_T_F(gsgph_rng *r, const gsgph_params *p, double *sym_val /* 4+nvar+num_constants */);
+
+/* initialize_population (:556-565) + tree_to_array (:675-693) for individuals n_seeds..P-1:
+ * tree t of individual n_seeds+t is pool[off[t] .. off[t]+len[t]).  Returns non-zero if cap is too small. */
+int gsgph_initialize_population(gsgph_rng *r, const gsgph_params *p, int32_t n_seeds, int32_t *pool,
+                                int32_t cap, int32_t *off, int32_t *len, int32_t *pool_len);
+
+/* one generation's decisions (:1447-1470): operator draw, tournament_selection (:830-840) on the OLD
+ * fit[], create_grow_tree_arrays (:609-639), mutation step (:919); elite slots only draw the operator */
+int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t index_best,
+                     gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t *pool_len);
+
+int32_t gsgph_best_individual(const gsgph_params *p, const double *fit);     /* :1180-1188 */
+
+/* Go fmt %v of a float64 (fitness / semantic output lines, main_cpu.go:123-126,1405-1409) */
+int gsgph_format_float(double v, char *buf, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -707,6 +707,9 @@ void orc_generation_replay(orc_state *s, const orc_plan_entry *plan, const int32
 /* ======================================================================== accessors ====== */
 
 void orc_keep_tree_semantics(orc_state *s, int flag) { s->keep_tree_sem = flag; }
+/* test hooks: drive the driver loop from a poked state (selection edge cases) */
+void orc_test_set_index_best(orc_state *s, int32_t b) { s->index_best = b; }
+void orc_test_set_generation(orc_state *s, int32_t g) { s->generation = g; }
 int32_t orc_generation_index(const orc_state *s) { return s->generation; }
 int32_t orc_index_best(const orc_state *s) { return s->index_best; }
 const double *orc_fit(const orc_state *s) { return s->fit; }

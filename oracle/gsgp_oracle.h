@@ -145,6 +145,8 @@ const double  *orc_symbol_values(const orc_state *s, int32_t *n_symbols);
 /* semantics of the random trees of individual `ind` in the last generation (proto dump fields) */
 const double  *orc_last_tree_semantic(const orc_state *s, int32_t ind, int32_t which);
 void           orc_keep_tree_semantics(orc_state *s, int flag);   /* off by default (O(P*N) memory) */
+void           orc_test_set_index_best(orc_state *s, int32_t b);  /* test hooks */
+void           orc_test_set_generation(orc_state *s, int32_t g);
 
 /* ------------------------------------------------------------------ formats -------------- */
 /* Go's fmt "%v" for float64 (shortest round-trip %g: exponent form when exp < -4 || exp >= 6). */

@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path through the C-ABI against the CPU oracle (run on the B200 box).
+
+Bars: tree semantics bit-exact (IEEE + - * / without contraction);
+GS-operator semantics and fitness within 1e-9 relative in fp64; parent indices, tree choices and
+the best index exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tests.util import synth_dataset, toy_fixture, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _engine_mod():
+    import go_gsgp_b200
+    return go_gsgp_b200
+
+
+def _mk(*a, **kw):
+    from tests.pair import make_pair
+    return make_pair(*a, **kw)
+
+
+def assert_close(a, b, tol=TOL, what=""):
+    e = rel_err(a, b)
+    assert np.all(e <= tol), f"{what}: max rel err {np.max(e):.3e} at {np.argmax(e)}"
+
+
+@pytest.mark.parametrize("n,nrow,v,depth,nconst", [
+    (1250, 1000, 5, 6, 0), (1254, 1003, 5, 8, 3), (100, 100, 3, 4, 0), (37, 5, 2, 6, 2), (4099, 2049, 20, 8, 0)])
+def test_tree_semantics_bitexact(n, nrow, v, depth, nconst):
+    g = _engine_mod()
+    X, y, _ = synth_dataset(1, n, v)
+    cfg = ob.make_config(population_size=4, max_depth_creation=depth, num_random_constants=nconst, rng_seed=7)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    trees = [o.create_grow_tree_arrays() for _ in range(300)]
+    trees.append(np.array([4], np.int32))                      # single terminal
+    with g.Engine(population_size=4, nvar=v, nrow=nrow, nrow_test=n - nrow, max_depth_creation=depth,
+                  num_constants=nconst) as e:
+        e.set_dataset(X, y)
+        e.set_constants(o.symbol_values())
+        got = e.eval_trees(trees)
+    for t, row in zip(trees, got):
+        want = o.semantic_evaluate_array(t)
+        assert np.array_equal(row, want, equal_nan=True), f"tree {list(t)[:12]}"
+
+
+def test_toy_fixture_kats():
+    g = _engine_mod()
+    X, y, nrow = toy_fixture()
+    with g.Engine(population_size=2, nvar=2, nrow=2, nrow_test=2) as e:
+        e.set_dataset(X, y)
+        e.set_constants(np.zeros(6))
+        sem = e.eval_trees([np.array([0, 3, 4, 4, 2, 7, 8, 5, 4], np.int32),
+                            np.array([3, 3, 4, 4, 1, 7, 8, 5, 5], np.int32),
+                            np.array([3, 3, 4, 4, 5], np.int32)])
+    np.testing.assert_array_equal(sem[0], X[:, 0] + X[:, 1] * X[:, 0])
+    np.testing.assert_array_equal(sem[1], np.ones(4))            # protected division
+    np.testing.assert_array_equal(sem[2], X[:, 0] / X[:, 1])
+
+
+def test_deep_tree_uses_local_stack():
+    g = _engine_mod()
+    X, y, _ = synth_dataset(1, 300, 4)
+    # right-deep chain of depth 20: (+ x0 (- x1 (* x2 (+ ...
+    depth = 20
+    t = []
+    for d in range(depth):
+        pos = len(t)
+        t += [d % 3, pos + 3, pos + 4, 4 + d % 4]
+    t.append(5)
+    t = np.array(t, np.int32)
+    cfg = ob.make_config(population_size=2)
+    o = ob.Oracle(cfg, X, y, 200)
+    o.create_T_F()
+    with g.Engine(population_size=2, nvar=4, nrow=200, nrow_test=100) as e:
+        e.set_dataset(X, y)
+        e.set_constants(o.symbol_values())
+        got = e.eval_trees([t])[0]
+    np.testing.assert_array_equal(got, o.semantic_evaluate_array(t))
+
+
+@pytest.mark.parametrize("measure", [ob.MSE, ob.RMSE, ob.MAE, ob.MRE])
+def test_initial_evaluate(measure):
+    X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=100, error_measure=measure)
+    assert_close(fit, o.fit(), 1e-12, "fit")
+    assert_close(fit_test, o.fit_test(), 1e-12, "fit_test")
+    assert best == o.index_best
+    for i in (0, 17, 99):
+        np.testing.assert_array_equal(e.get_semantic(i), o.semantic(i))
+    e.close()
+
+
+def _lockstep_replay(o, e, gens, tol=TOL, check_sem_every=1):
+    for g in range(gens):
+        o.generation()
+        plan, pool = o.last_plan(), o.last_tree_pool()
+        fit, fit_test, best = e.generation(plan, pool)
+        assert_close(fit, o.fit(), tol, f"gen {g} fit")
+        assert_close(fit_test, o.fit_test(), tol, f"gen {g} fit_test")
+        assert best == o.index_best, f"gen {g} best"
+        if g % check_sem_every == 0:
+            for i in range(0, o.P, max(1, o.P // 16)):
+                assert_close(e.get_semantic(i), o.semantic(i), tol, f"gen {g} sem[{i}]")
+
+
+def test_config1_replay_lockstep():
+    """BASELINE config 1 (5 vars x 1000/250 cases, pop 100), host-replay mode, generation by generation."""
+    X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
+    o, e, _ = _mk(X, y, nrow, population_size=100, seed=1)
+    _lockstep_replay(o, e, 100, check_sem_every=10)
+    assert_close(e.get_semantics(), o.semantics(), TOL, "final semantics")
+    bf, bt, bi = e.get_history(0, 101)
+    assert bi[-1] == o.index_best and rel_err(bf[-1], o.fit()[o.index_best]) <= TOL
+    assert np.all(np.diff(bf) <= 0), "elitism: best train fitness never gets worse"
+    e.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(population_size=64, error_measure=ob.MAE, num_random_constants=4, max_depth_creation=8),
+    dict(population_size=50, error_measure=ob.MSE, minimization_problem=0, tournament_size=7),
+    dict(population_size=33, error_measure=ob.MRE, p_crossover=0.0, p_mutation=1.0, zero_depth=1),
+    dict(population_size=40, error_measure=ob.RMSE, p_crossover=1.0, p_mutation=0.0, init_type=0),
+    dict(population_size=20, error_measure=ob.RMSE, p_crossover=0.0, p_mutation=0.0, init_type=1),
+])
+def test_replay_lockstep_variants(kw):
+    X, y, nrow = synth_dataset(2, 777, 6, nrow=533)
+    o, e, _ = _mk(X, y, nrow, seed=3, **kw)
+    _lockstep_replay(o, e, 12)
+    e.close()
+
+
+def test_replay_chunked_workspace_and_tree_semantics():
+    g = _engine_mod()
+    X, y, nrow = synth_dataset(1, 2100, 5, nrow=1500)
+    # tiny workspace -> several interp+gsop launch pairs per generation
+    o, e, _ = _mk(X, y, nrow, population_size=30, seed=5, workspace_bytes=5 * 2 * 2112 * 8)
+    _lockstep_replay(o, e, 4)
+    e.close()
+    o, e, _ = _mk(X, y, nrow, population_size=30, seed=5, flags=g.capi.FLAG_KEEP_TREE_SEMANTICS)
+    o.keep_tree_semantics(True)
+    _lockstep_replay(o, e, 2)
+    plan = o.last_plan()
+    for k in range(30):
+        if plan["tree0_len"][k] > 0:
+            np.testing.assert_array_equal(e.get_tree_semantic(k, 0), o.last_tree_semantic(k, 0))
+            np.testing.assert_array_equal(e.get_tree(k, 0), o.last_tree_pool()[plan["tree0_off"][k]:][:plan["tree0_len"][k]])
+        if plan["tree1_len"][k] > 0:
+            np.testing.assert_array_equal(e.get_tree_semantic(k, 1), o.last_tree_semantic(k, 1))
+    e.close()
+
+
+def test_semantic_feeding_seeds():
+    X, y, nrow = synth_dataset(3, 900, 5, nrow=700)
+    rng = np.random.default_rng(3)
+    seeds = [y + rng.normal(0, 0.05 + 0.001 * k, size=900) for k in range(8)]
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=24, seeds=seeds, seed=2)
+    assert_close(fit, o.fit(), 1e-12, "seeded fit")
+    assert best == o.index_best and best < 8
+    _lockstep_replay(o, e, 8)
+    e.close()
+
+
+def test_sigmoid_quirks_through_crossover_and_mutation():
+    """exp64's overflow / tiny-argument rules (main_cpu.go:50-61) reached through constant trees."""
+    g = _engine_mod()
+    X, y, nrow = synth_dataset(1, 64, 2, nrow=48)
+    consts = [0.0, 1e-17, -1e-17, 800.0, -800.0, np.inf, -np.inf, np.nan, 2.0 ** -53, -(2.0 ** -54), 0.3, -745.2]
+    P = len(consts) * 2
+    cfg = ob.make_config(population_size=P, num_random_constants=len(consts), error_measure=ob.RMSE)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    sv = o.symbol_values()
+    sv[6:] = consts
+    # the oracle keeps its symbol values internally: write through the returned pointer
+    n = __import__("ctypes").c_int32()
+    p = o.L.orc_symbol_values(o.h, n)
+    for i, c in enumerate(consts):
+        p[6 + i] = c
+    rng = np.random.default_rng(9)
+    seeds = [rng.normal(size=64) for _ in range(P)]
+    e = g.Engine(population_size=P, nvar=2, nrow=nrow, nrow_test=64 - nrow, num_constants=len(consts),
+                 error_measure=ob.RMSE)
+    e.set_dataset(X, y)
+    e.set_constants(sv)
+    for i, s in enumerate(seeds):
+        o.seed_semantic(i, s); e.seed_semantic(i, s)
+    o.initialize_population(P)
+    o.evaluate()
+    e.fitness_all()
+    plan = np.zeros(P, ob.PLAN_DTYPE)
+    pool = []
+    for k in range(P):
+        c = k % len(consts)
+        plan[k] = (ob.OP_XO if k < len(consts) else ob.OP_MUT, 0, (k + 1) % P, (k + 2) % P,
+                   len(pool), 1, -1, 0, 0.37)
+        pool.append(6 + c)
+        if k >= len(consts):
+            plan[k]["tree1_off"], plan[k]["tree1_len"] = len(pool), 1
+            pool.append(6 + (c + 3) % len(consts))
+    pool = np.array(pool, np.int32)
+    o.generation_replay(plan, pool)
+    fit, fit_test, best = e.generation(plan, pool)
+    got, want = e.get_semantics(), o.semantics()
+    assert_close(got, want, TOL, "quirk semantics")
+    # the cases the quirks decide are exact: sigma in {0.5, 1.0, 1/MaxFloat64}
+    for k in range(7):
+        np.testing.assert_array_equal(got[k], want[k])
+    assert_close(fit, o.fit(), TOL, "quirk fit")
+    assert best == o.index_best
+    e.close()
+
+
+def test_device_mode_lockstep():
+    """On-device selection + random trees on Philox streams vs the oracle drawing the same streams."""
+    X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
+    for kw in (dict(population_size=100), dict(population_size=37, num_random_constants=5, max_depth_creation=8,
+                                               tournament_size=3, p_crossover=0.3, p_mutation=0.5)):
+        o, e, _ = _mk(X, y, nrow, rng_kind=ob.RNG_PHILOX, seed=11, **kw)
+        for g in range(25):
+            o.generation()
+            e.run_generations(1)
+            want, got = o.last_plan(), e.get_plan()
+            for f in ("op", "elite", "p1", "p2", "tree0_len", "tree1_len"):
+                np.testing.assert_array_equal(got[f], want[f], err_msg=f"gen {g} plan.{f}")
+            np.testing.assert_array_equal(got["ms"], want["ms"])
+            pool = o.last_tree_pool()
+            for k in range(0, o.P, 7):
+                for w, (off, ln) in enumerate((("tree0_off", "tree0_len"), ("tree1_off", "tree1_len"))):
+                    if want[ln][k]:
+                        np.testing.assert_array_equal(e.get_tree(k, w), pool[want[off][k]:][:want[ln][k]])
+            fit, fit_test, best = e.get_fitness()
+            assert_close(fit, o.fit(), TOL, f"gen {g} fit")
+            assert_close(fit_test, o.fit_test(), TOL, f"gen {g} fit_test")
+            assert best == o.index_best
+        assert_close(e.get_semantics(), o.semantics(), TOL, "device-mode semantics")
+        e.close()
+
+
+def test_device_mode_multi_generation_run_matches_stepwise():
+    X, y, nrow = synth_dataset(1, 640, 5, nrow=512)
+    o, e, _ = _mk(X, y, nrow, population_size=48, rng_kind=ob.RNG_PHILOX, seed=4)
+    for _ in range(10):
+        o.generation()
+    e.run_generations(10)
+    fit, fit_test, best = e.get_fitness()
+    assert_close(fit, o.fit(), TOL, "fit after 10 async generations")
+    assert best == o.index_best and e.generation_index == 10
+    bf, bt, bi = e.get_history(0, 11)
+    assert bi[10] == best
+    e.close()
+
+
+def test_selection_with_nan_and_ties():
+    """Tournament (:830-840) and best_individual (:1180-1188) on fitness tables with exact ties,
+    -0.0/0.0 and NaNs: the device plan must equal the oracle's, draw for draw."""
+    import ctypes as C
+    X, y, nrow = synth_dataset(1, 64, 3, nrow=48)
+    P = 40
+    for minimize in (1, 0):
+        o, e, _ = _mk(X, y, nrow, population_size=P, rng_kind=ob.RNG_PHILOX, seed=21, minimization_problem=minimize)
+        o.L.orc_test_set_index_best.argtypes = [C.c_void_p, C.c_int32]
+        o.L.orc_test_set_generation.argtypes = [C.c_void_p, C.c_int32]
+        rng = np.random.default_rng(5)
+        fit = np.round(rng.uniform(0, 3, size=P), 1)                 # many exact ties
+        fit[[3, 9, 10]] = np.nan
+        fit[5] = -0.0
+        fit[6] = 0.0
+        for trial in range(3):
+            if trial == 1:
+                fit[0] = np.nan                                   # a NaN at index 0 is never beaten
+            if trial == 2:
+                fit[:] = np.nan
+            np.ctypeslib.as_array(o.L.orc_fit(o.h), (P,))[:] = fit   # poke the oracle's fit[] table
+            best = o.L.orc_best_individual(o.h)
+            o.L.orc_test_set_index_best(o.h, best)
+            o.L.orc_test_set_generation(o.h, trial)               # next generation draws streams (trial+1, k)
+            e.set_fitness(fit, fit)
+            assert e.get_fitness()[2] == best
+            got = e.draw_plan(trial + 1)
+            o.generation()
+            want = o.last_plan()
+            for f in ("op", "elite", "p1", "p2", "tree0_len", "tree1_len"):
+                np.testing.assert_array_equal(got[f], want[f], err_msg=f"trial {trial} plan.{f}")
+        e.close()
+
+
+def test_error_behaviour():
+    g = _engine_mod()
+    with pytest.raises(g.GsgpError):
+        g.Engine(population_size=10, nvar=2, nrow=2, nrow_test=2, p_crossover=0.8, p_mutation=0.5)
+    X, y, nrow = toy_fixture()
+    with g.Engine(population_size=2, nvar=2, nrow=2, nrow_test=2) as e:
+        with pytest.raises(g.GsgpError):
+            e.fitness_all()                                   # dataset not set
+        e.set_dataset(X, y)
+        e.set_constants(np.zeros(6))
+        with pytest.raises(g.GsgpError):
+            e.eval_trees([np.array([0, 3, 9, 4, 5], np.int32)])     # child index out of range
+        with pytest.raises(g.GsgpError):
+            e.eval_trees([np.array([0, 0, 0], np.int32)])           # cycle
+        with pytest.raises(g.GsgpError):
+            e.eval_trees([np.array([77], np.int32)])                # unknown symbol
+        plan = np.zeros(2, ob.PLAN_DTYPE)
+        with pytest.raises(g.GsgpError):
+            e.generation(plan, np.zeros(1, np.int32))               # not evaluated yet
+        e.eval_initial(0, [np.array([4], np.int32), np.array([5], np.int32)])
+        e.fitness_all()
+        plan["op"] = ob.OP_XO; plan["p1"] = 5
+        with pytest.raises(g.GsgpError):
+            e.generation(plan, np.zeros(1, np.int32))               # parent out of range
+        with pytest.raises(g.GsgpError):
+            e.run_generations(1)                                    # replay-mode context

@@ -1,0 +1,62 @@
+"""The C++ host-side driver pieces (include/gsgp_host.h) against the oracle's restatement of the
+same reference code: two independent implementations of main_cpu.go's RNG-order-defining logic must
+produce identical constants, initial trees and generation plans from the same seed."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tests.util import synth_dataset
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from go_gsgp_b200 import build
+    build.build()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(population_size=100),
+    dict(population_size=57, num_random_constants=6, max_depth_creation=8, tournament_size=3, zero_depth=1),
+    dict(population_size=30, init_type=0, p_crossover=0.2, p_mutation=0.7, minimization_problem=0),
+    dict(population_size=30, init_type=1, max_depth_creation=4),
+])
+def test_host_plan_equals_oracle_plan(kw):
+    from go_gsgp_b200.host import HostDriver
+    X, y, nrow = synth_dataset(1, 200, 5, nrow=150)
+    cfg = ob.make_config(rng_kind=ob.RNG_ALFG, rng_seed=9, **kw)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    h = HostDriver(nvar=5, seed=9, population_size=kw["population_size"],
+                   num_constants=kw.get("num_random_constants", 0),
+                   max_depth_creation=kw.get("max_depth_creation", 6), tournament_size=kw.get("tournament_size", 4),
+                   zero_depth=kw.get("zero_depth", 0), minimization_problem=kw.get("minimization_problem", 1),
+                   init_type=kw.get("init_type", 2), p_crossover=kw.get("p_crossover", 0.6),
+                   p_mutation=kw.get("p_mutation", 0.3))
+    np.testing.assert_array_equal(h.create_T_F(), o.symbol_values())
+    o.initialize_population(0)
+    trees = h.initialize_population(0)
+    assert len(trees) == o.P
+    for i, t in enumerate(trees):
+        np.testing.assert_array_equal(t, o.initial_tree(i))
+    o.evaluate()
+    for g in range(6):
+        fit, best = o.fit(), o.index_best
+        assert h.best_individual(fit) == best
+        plan, pool = h.build_plan(fit, best)
+        o.generation()
+        want = o.last_plan()
+        for f in want.dtype.names:
+            np.testing.assert_array_equal(plan[f], want[f], err_msg=f"gen {g} {f}")
+        np.testing.assert_array_equal(pool[: len(o.last_tree_pool())], o.last_tree_pool())
+
+
+def test_format_float_matches_go_v():
+    from go_gsgp_b200.host import format_float as f
+    rng = np.random.default_rng(0)
+    vals = list(rng.normal(size=200)) + list(10.0 ** rng.uniform(-30, 30, size=200)) + [
+        0.0, -0.0, 1.0, 100000.0, 1e6, 1e-4, 1e-5, 5e-324, 1.7976931348623157e308, float("nan"), float("inf"), -float("inf")]
+    for v in vals:
+        assert f(v) == ob.format_float(v)
+        if np.isfinite(v):
+            assert float(f(v)) == v
+    assert f(1e6) == "1e+06" and f(123456.0) == "123456" and f(0.5) == "0.5"
