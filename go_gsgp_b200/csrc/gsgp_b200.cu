@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -112,19 +113,22 @@ struct gsgp_ctx {
     double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
     gsgp_plan_entry *dplan = nullptr;
     int32_t *dtree_pool = nullptr;                            // device mode
-    DevBuf<uint16_t> dprog_pool;
-    int32_t *dprog_off = nullptr, *dprog_len = nullptr, *dprog_maxsp = nullptr;
+    DevBuf<Ins> dprog_pool;                                   // accumulator programs (program.hpp)
+    uint16_t *dpost_pool = nullptr;                           // device mode: postfix scratch of plan_kernel
+    int32_t *dprog_off = nullptr, *dprog_len = nullptr;
+    int32_t post_stride = 0;
+    int32_t interp_cpt = 4, interp_tile = 256;                // tunables (GSGP_INTERP_CPT / GSGP_INTERP_TILE)
+    int sm_count = 148;
     int32_t *dindex_best = nullptr;
     BestRec *dhist = nullptr; int32_t hist_cap = 0;
 
     PinnedBuf<gsgp_plan_entry> hplan;
-    PinnedBuf<uint16_t> hprog;
+    PinnedBuf<Ins> hprog;
     PinnedBuf<int32_t> hoff, hlen;
     PinnedBuf<double> hfit;
     PinnedBuf<int32_t> hint;
     std::vector<int32_t> last_pool;                           // replay mode: last generation's trees
     std::vector<gsgp_plan_entry> last_plan;
-    int32_t last_maxsp = 0;
 
     ncclComm_t comm = nullptr;
     ProfSlot prof[GSGP_K_COUNT];
@@ -173,22 +177,56 @@ struct ProfScope {                 // CUDA-event bracket around one kernel launc
 
 // ---- launches ---------------------------------------------------------------------------------
 
-int launch_interp(gsgp_ctx *c, const uint16_t *prog_pool, const int32_t *prog_off, const int32_t *prog_len,
-                  int32_t first_slot, int32_t n_slots, int32_t max_sp, double *out, int64_t out_pitch,
+// launch geometry of the interpreter: case tile (staged in shared memory when the variable columns of
+// a tile fit), tree-slot groups so that the grid covers the SMs several times over
+struct InterpGeom { int32_t tile; bool stage; size_t smem; int32_t groups, slots_per_group; };
+
+InterpGeom interp_geometry(const gsgp_ctx *c, int32_t n_slots, int32_t levels)
+{
+    InterpGeom g{};
+    const size_t fixed = (size_t)kInterpWarps * levels * c->interp_cpt * 32 * sizeof(double) +
+                         (size_t)kInterpWarps * kProgSmem * sizeof(Ins) + 16;
+    g.tile = 256; g.stage = false;
+    for (int32_t t : {c->interp_tile, 128}) {
+        if ((size_t)c->cfg.nvar * t * sizeof(double) + fixed <= (size_t)110 * 1024) { g.tile = t; g.stage = true; break; }
+    }
+    g.smem = fixed + (g.stage ? (size_t)c->cfg.nvar * g.tile * sizeof(double) : 0);
+    const int32_t n_tiles = (c->L.n_pad + g.tile - 1) / g.tile;
+    const int32_t target = c->sm_count * 8;
+    int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
+    groups = std::min(groups, std::max(1, (n_slots + 15) / 16));
+    groups = std::min(groups, 65535);
+    g.slots_per_group = (n_slots + groups - 1) / groups;
+    g.groups = (n_slots + g.slots_per_group - 1) / g.slots_per_group;
+    return g;
+}
+
+template <int CPT>
+cudaError_t interp_dispatch(const InterpGeom &g, dim3 grid, cudaStream_t st, const InterpArgs &a)
+{
+    if (g.stage) interp_kernel<CPT, true><<<grid, kInterpThreads, g.smem, st>>>(a);
+    else interp_kernel<CPT, false><<<grid, kInterpThreads, g.smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+int launch_interp(gsgp_ctx *c, const Ins *prog_pool, const int32_t *prog_off, const int32_t *prog_len,
+                  int32_t first_slot, int32_t n_slots, int32_t stack_need, double *out, int64_t out_pitch,
                   double n_trees_hint)
 {
     if (n_slots <= 0) return 0;
+    if (stack_need > kMaxStackLevels) return fail(c, "tree needs %d spill levels > %d", stack_need, kMaxStackLevels);
+    const int32_t levels = std::max(1, stack_need);
+    const InterpGeom g = interp_geometry(c, n_slots, levels);
+    if (g.smem > (size_t)227 * 1024) return fail(c, "interpreter needs %zu bytes of shared memory", g.smem);
     InterpArgs a{};
     a.prog_pool = prog_pool; a.prog_off = prog_off; a.prog_len = prog_len;
-    a.first_slot = first_slot; a.n_slots = n_slots;
+    a.first_slot = first_slot; a.n_slots = n_slots; a.slots_per_group = g.slots_per_group;
     a.X = c->dX; a.sym_val = c->dsym; a.nvar = c->cfg.nvar;
     a.out = out; a.out_pitch = out_pitch; a.L = c->L;
-    dim3 grid((c->L.n_pad + kInterpTile - 1) / kInterpTile, (n_slots + kInterpWarps - 1) / kInterpWarps);
+    a.tile = g.tile; a.stack_levels = levels;
+    dim3 grid((c->L.n_pad + g.tile - 1) / g.tile, g.groups);
     ProfScope ps(c, GSGP_K_INTERP, n_trees_hint * 8.0 * (double)(c->L.n_tr + c->L.n_te));
-    if (max_sp <= kRegStack) interp_kernel<kRegStack, false><<<grid, kInterpThreads, 0, c->stream>>>(a);
-    else if (max_sp <= kDeepStack) interp_kernel<1, true><<<grid, kInterpThreads, 0, c->stream>>>(a);
-    else return fail(c, "tree needs an operand stack of %d > %d", max_sp, kDeepStack);
-    CU(c, cudaGetLastError());
+    CU(c, c->interp_cpt == 2 ? interp_dispatch<2>(g, grid, c->stream, a) : interp_dispatch<4>(g, grid, c->stream, a));
     return 0;
 }
 
@@ -304,8 +342,8 @@ int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may 
 int launch_plan(gsgp_ctx *c, int32_t generation)
 {
     PlanArgs a{};
-    a.plan = c->dplan; a.tree_pool = c->dtree_pool; a.prog_pool = c->dprog_pool.p;
-    a.prog_len = c->dprog_len; a.prog_maxsp = c->dprog_maxsp;
+    a.plan = c->dplan; a.tree_pool = c->dtree_pool; a.post_pool = c->dpost_pool; a.prog_pool = c->dprog_pool.p;
+    a.prog_len = c->dprog_len; a.post_stride = c->post_stride;
     a.fit = c->dfit[c->cur]; a.index_best = c->dindex_best;
     a.P = c->cfg.population_size; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
     a.max_depth = c->cfg.max_depth_creation; a.zero_depth = c->cfg.zero_depth;
@@ -319,22 +357,30 @@ int launch_plan(gsgp_ctx *c, int32_t generation)
     return 0;
 }
 
-// host trees (reference array format) -> postfix programs in pinned staging; returns max stack need
+// host trees (reference array format) -> accumulator programs; returns the spill levels they need
 int stage_programs(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len, const int32_t *off,
-                   const int32_t *len, std::vector<uint16_t> &progs, int32_t *hoff, int32_t *hlen, int32_t &max_sp)
+                   const int32_t *len, std::vector<Ins> &progs, int32_t *hoff, int32_t *hlen, int32_t &stack_need)
 {
     progs.clear();
-    max_sp = 0;
+    stack_need = 0;
     std::string err;
+    std::vector<uint16_t> post, abs_stack;
     for (int32_t t = 0; t < n; ++t) {
         if (len[t] <= 0 || off[t] < 0) { hoff[t] = 0; hlen[t] = 0; continue; }
         if ((int64_t)off[t] + len[t] > pool_len) return fail(c, "tree %d exceeds the tree pool", t);
-        const size_t start = progs.size();
+        post.clear();
         int32_t sp = 0;
-        if (!prefix_to_postfix(pool + off[t], len[t], c->n_symbols, progs, sp, err))
+        if (!prefix_to_postfix(pool + off[t], len[t], c->n_symbols, post, sp, err))
             return fail(c, "tree %d: %s", t, err.c_str());
-        hoff[t] = (int32_t)start; hlen[t] = (int32_t)(progs.size() - start);
-        max_sp = std::max(max_sp, sp);
+        const size_t start = progs.size();
+        progs.resize(start + post.size() / 2 + 1);
+        abs_stack.resize((size_t)sp + 1);
+        int n_ins = 0, need = 0;
+        if (!compile_postfix(post.data(), (int)post.size(), progs.data() + start, n_ins, need, abs_stack.data(), (int)abs_stack.size()))
+            return fail(c, "tree %d: cannot compile", t);
+        progs.resize(start + n_ins);
+        hoff[t] = (int32_t)start; hlen[t] = n_ins;
+        stack_need = std::max(stack_need, need);
     }
     return 0;
 }
@@ -396,7 +442,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     if (cfg->tournament_size < 1) return fail(nullptr, "tournament_size must be >= 1");
     if (cfg->p_crossover < 0 || cfg->p_mutation < 0 || cfg->p_crossover + cfg->p_mutation > 1)   // main_cpu.go:374-376
         return fail(nullptr, "Crossover rate and mutation rate must be greater or equal to 0 and their sum must be smaller or equal to 1.");
-    if (4 + (int64_t)cfg->nvar + cfg->num_constants > 0xFFFF) return fail(nullptr, "too many symbols");
+    if (4 + (int64_t)cfg->nvar + cfg->num_constants > kMaxSymbols) return fail(nullptr, "too many symbols");
     if (cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX && (cfg->max_depth_creation < 1 || cfg->max_depth_creation > kMaxGenDepth))
         return fail(nullptr, "device RNG mode supports max_depth_creation in [1,%d]", kMaxGenDepth);
 
@@ -423,7 +469,20 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
 
     const int P = cfg->population_size;
     const size_t row = (size_t)c->L.n_pad;
-    CUC(cudaMalloc((void **)&c->dX, sizeof(double) * row * cfg->nvar));
+    {
+        cudaDeviceProp prop{};
+        CUC(cudaGetDeviceProperties(&prop, cfg->device));
+        c->sm_count = prop.multiProcessorCount;
+        if (const char *e = getenv("GSGP_INTERP_CPT")) c->interp_cpt = (atoi(e) == 2) ? 2 : 4;
+        if (const char *e = getenv("GSGP_INTERP_TILE")) { int t = atoi(e); if (t >= 128 && t <= 2048 && t % 128 == 0) c->interp_tile = t; }
+        const int kMaxSmem = 227 * 1024;
+        CUC(cudaFuncSetAttribute(interp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(interp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(interp_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(interp_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    }
+    // +64 doubles of slack: the unstaged 4-cases-per-lane path may read (never use) past the last tile
+    CUC(cudaMalloc((void **)&c->dX, sizeof(double) * (row * cfg->nvar + 64)));
     CUC(cudaMalloc((void **)&c->dy, sizeof(double) * row));
     CUC(cudaMalloc((void **)&c->dsym, sizeof(double) * (size_t)c->n_symbols));
     CUC(cudaMemsetAsync(c->dX, 0, sizeof(double) * row * cfg->nvar, c->stream));
@@ -444,16 +503,17 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMemsetAsync(c->dplan, 0, sizeof(gsgp_plan_entry) * P, c->stream));
     CUC(cudaMalloc((void **)&c->dprog_off, sizeof(int32_t) * 2 * P));
     CUC(cudaMalloc((void **)&c->dprog_len, sizeof(int32_t) * 2 * P));
-    CUC(cudaMalloc((void **)&c->dprog_maxsp, sizeof(int32_t) * 2 * P));
     CUC(cudaMemsetAsync(c->dprog_len, 0, sizeof(int32_t) * 2 * P, c->stream));
     CUC(cudaMalloc((void **)&c->dindex_best, sizeof(int32_t)));
     CUC(cudaMemsetAsync(c->dindex_best, 0, sizeof(int32_t), c->stream));
 
     if (cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX) {
         const int d = cfg->max_depth_creation;
-        c->prog_stride = (1 << (d + 1));                       // nodes <= 2^(d+1)-1
+        c->post_stride = (1 << (d + 1));                       // nodes <= 2^(d+1)-1
+        c->prog_stride = (1 << d);                             // function nodes <= 2^d-1
         c->tree_stride = 4 * (1 << d);                         // ints  <= 4*2^d-3 (main_cpu.go:609-639)
         CUC(cudaMalloc((void **)&c->dtree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
+        CUC(cudaMalloc((void **)&c->dpost_pool, sizeof(uint16_t) * 2 * (size_t)P * c->post_stride));
         CUC(c->dprog_pool.reserve((size_t)2 * P * c->prog_stride));
         std::vector<int32_t> off(2 * (size_t)P);
         for (int t = 0; t < 2 * P; ++t) off[t] = t * c->prog_stride;
@@ -499,7 +559,7 @@ void gsgp_destroy(gsgp_ctx *c)
     for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
     cudaFree(c->dplan); cudaFree(c->dtree_pool); cudaFree(c->dprog_off); cudaFree(c->dprog_len);
-    cudaFree(c->dprog_maxsp); cudaFree(c->dindex_best); cudaFree(c->dhist);
+    cudaFree(c->dpost_pool); cudaFree(c->dindex_best); cudaFree(c->dhist);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -574,19 +634,16 @@ int gsgp_seed_semantic(gsgp_ctx *c, int32_t ind, const double *sem)
 static int eval_trees_into(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len, const int32_t *off,
                            const int32_t *len, double *dout, int64_t pitch)
 {
-    std::vector<uint16_t> progs;
+    std::vector<Ins> progs;
     std::vector<int32_t> hoff(n), hlen(n);
     int32_t max_sp = 0;
     if (stage_programs(c, n, pool, pool_len, off, len, progs, hoff.data(), hlen.data(), max_sp)) return 1;
-    DevBuf<uint16_t> dp; DevBuf<int32_t> doff, dlen;
+    DevBuf<Ins> dp; DevBuf<int32_t> doff, dlen;
     CU(c, dp.reserve(progs.size())); CU(c, doff.reserve(n)); CU(c, dlen.reserve(n));
-    CU(c, cudaMemcpyAsync(dp.p, progs.data(), sizeof(uint16_t) * progs.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dp.p, progs.data(), sizeof(Ins) * progs.size(), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(doff.p, hoff.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dlen.p, hlen.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
-    for (int32_t t0 = 0; t0 < n; t0 += 65535 * kInterpWarps) {
-        const int32_t nt = std::min<int32_t>(n - t0, 65535 * kInterpWarps);
-        if (launch_interp(c, dp.p, doff.p, dlen.p, t0, nt, max_sp, dout + (int64_t)t0 * pitch, pitch, nt)) return 1;
-    }
+    if (launch_interp(c, dp.p, doff.p, dlen.p, 0, n, max_sp, dout, pitch, n)) return 1;
     CU(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -678,14 +735,14 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
         off[2 * k + 1] = t1 ? e.tree1_off : -1; len[2 * k + 1] = t1 ? e.tree1_len : 0;
         c->hplan.p[k] = e;
     }
-    std::vector<uint16_t> progs;
+    std::vector<Ins> progs;
     int32_t max_sp = 0;
     if (stage_programs(c, 2 * P, tree_pool, pool_len, off.data(), len.data(), progs, c->hoff.p, c->hlen.p, max_sp)) return 1;
     CU(c, c->hprog.reserve(progs.size()));
-    memcpy(c->hprog.p, progs.data(), sizeof(uint16_t) * progs.size());
+    memcpy(c->hprog.p, progs.data(), sizeof(Ins) * progs.size());
     CU(c, c->dprog_pool.reserve(progs.size()));
     CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->dprog_pool.p, c->hprog.p, sizeof(uint16_t) * progs.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->dprog_pool.p, c->hprog.p, sizeof(Ins) * progs.size(), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->dprog_off, c->hoff.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->dprog_len, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
     if (run_generation_kernels(c, c->hplan.p, max_sp)) return 1;
@@ -699,7 +756,7 @@ int gsgp_run_generations(gsgp_ctx *c, int32_t n)
     if (check_ready(c)) return 1;
     if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_run_generations needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
     if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
-    const int32_t max_sp = c->cfg.max_depth_creation + 1;
+    const int32_t max_sp = std::max(1, c->cfg.max_depth_creation - 1);   // spill levels <= depth of a TT node
     if (ensure_hist(c, c->generation + n)) return 1;
     for (int32_t g = 0; g < n; ++g) {
         if (launch_plan(c, c->generation + 1)) return 1;
