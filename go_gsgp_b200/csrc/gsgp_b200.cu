@@ -115,9 +115,10 @@ struct gsgp_ctx {
     int32_t *dtree_pool = nullptr;                            // device mode
     DevBuf<Ins> dprog_pool;                                   // accumulator programs (program.hpp)
     uint16_t *dpost_pool = nullptr;                           // device mode: postfix scratch of plan_kernel
+    uint32_t *dcompile_scratch = nullptr;                     // device mode: program-builder scratch
     int32_t *dprog_off = nullptr, *dprog_len = nullptr;
     int32_t post_stride = 0;
-    int32_t interp_cpt = 4, interp_tile = 256;                // tunables (GSGP_INTERP_CPT / GSGP_INTERP_TILE)
+    int32_t interp_tile = 256;                                // tunable (GSGP_INTERP_TILE)
     int sm_count = 148;
     int32_t *dindex_best = nullptr;
     BestRec *dhist = nullptr; int32_t hist_cap = 0;
@@ -179,54 +180,52 @@ struct ProfScope {                 // CUDA-event bracket around one kernel launc
 
 // launch geometry of the interpreter: case tile (staged in shared memory when the variable columns of
 // a tile fit), tree-slot groups so that the grid covers the SMs several times over
+constexpr int32_t kMaxGroupSlots = 1024;
 struct InterpGeom { int32_t tile; bool stage; size_t smem; int32_t groups, slots_per_group; };
 
 InterpGeom interp_geometry(const gsgp_ctx *c, int32_t n_slots, int32_t levels)
 {
     InterpGeom g{};
-    const size_t fixed = (size_t)kInterpWarps * levels * c->interp_cpt * 32 * sizeof(double) +
-                         (size_t)kInterpWarps * kProgSmem * sizeof(Ins) + 16;
+    const size_t fixed = (size_t)kInterpWarps * 2 * kProgSmem * sizeof(Ins) + 64;
+    const size_t spill = (size_t)kInterpWarps * levels * kPass * sizeof(double);
+    const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
     g.tile = 256; g.stage = false;
-    for (int32_t t : {c->interp_tile, 128}) {
-        if ((size_t)c->cfg.nvar * t * sizeof(double) + fixed <= (size_t)110 * 1024) { g.tile = t; g.stage = true; break; }
+    for (int32_t t : {c->interp_tile, 256}) {
+        if (ncol * t * sizeof(double) + spill + fixed <= (size_t)96 * 1024) { g.tile = t; g.stage = true; break; }
     }
-    g.smem = fixed + (g.stage ? (size_t)c->cfg.nvar * g.tile * sizeof(double) : 0);
     const int32_t n_tiles = (c->L.n_pad + g.tile - 1) / g.tile;
     const int32_t target = c->sm_count * 8;
     int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
     groups = std::min(groups, std::max(1, (n_slots + 15) / 16));
-    groups = std::min(groups, 65535);
+    groups = std::max(groups, (n_slots + kMaxGroupSlots - 1) / kMaxGroupSlots);   // slot table lives in shared memory
     g.slots_per_group = (n_slots + groups - 1) / groups;
     g.groups = (n_slots + g.slots_per_group - 1) / g.slots_per_group;
+    g.smem = fixed + 8 * (size_t)g.slots_per_group + (g.stage ? ncol * g.tile * sizeof(double) + spill : 0);
     return g;
 }
 
-template <int CPT>
-cudaError_t interp_dispatch(const InterpGeom &g, dim3 grid, cudaStream_t st, const InterpArgs &a)
-{
-    if (g.stage) interp_kernel<CPT, true><<<grid, kInterpThreads, g.smem, st>>>(a);
-    else interp_kernel<CPT, false><<<grid, kInterpThreads, g.smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-int launch_interp(gsgp_ctx *c, const Ins *prog_pool, const int32_t *prog_off, const int32_t *prog_len,
+int launch_interp(gsgp_ctx *c, const Ins *prog_pool, const int32_t *prog_off, const int32_t *prog_desc,
                   int32_t first_slot, int32_t n_slots, int32_t stack_need, double *out, int64_t out_pitch,
                   double n_trees_hint)
 {
     if (n_slots <= 0) return 0;
     if (stack_need > kMaxStackLevels) return fail(c, "tree needs %d spill levels > %d", stack_need, kMaxStackLevels);
-    const int32_t levels = std::max(1, stack_need);
+    // spill levels kept in shared memory: what the launch needs, at most kMaxSmemLevels (deeper trees,
+    // ~1 in 10^4 with Sethi-Ullman ordering, take the generic path)
+    const int32_t levels = std::max(1, std::min(stack_need, kMaxSmemLevels));
     const InterpGeom g = interp_geometry(c, n_slots, levels);
-    if (g.smem > (size_t)227 * 1024) return fail(c, "interpreter needs %zu bytes of shared memory", g.smem);
+    if (g.groups > 65535) return fail(c, "too many tree slots in one launch (%d)", n_slots);
     InterpArgs a{};
-    a.prog_pool = prog_pool; a.prog_off = prog_off; a.prog_len = prog_len;
+    a.prog_pool = prog_pool; a.prog_off = prog_off; a.prog_desc = prog_desc;
     a.first_slot = first_slot; a.n_slots = n_slots; a.slots_per_group = g.slots_per_group;
-    a.X = c->dX; a.sym_val = c->dsym; a.nvar = c->cfg.nvar;
+    a.X = c->dX; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
     a.out = out; a.out_pitch = out_pitch; a.L = c->L;
-    a.tile = g.tile; a.stack_levels = levels;
+    a.tile = g.tile; a.smem_levels = levels;
     dim3 grid((c->L.n_pad + g.tile - 1) / g.tile, g.groups);
     ProfScope ps(c, GSGP_K_INTERP, n_trees_hint * 8.0 * (double)(c->L.n_tr + c->L.n_te));
-    CU(c, c->interp_cpt == 2 ? interp_dispatch<2>(g, grid, c->stream, a) : interp_dispatch<4>(g, grid, c->stream, a));
+    if (g.stage) interp_kernel<true><<<grid, kInterpThreads, g.smem, c->stream>>>(a);
+    else interp_kernel<false><<<grid, kInterpThreads, g.smem, c->stream>>>(a);
+    CU(c, cudaGetLastError());
     return 0;
 }
 
@@ -343,7 +342,8 @@ int launch_plan(gsgp_ctx *c, int32_t generation)
 {
     PlanArgs a{};
     a.plan = c->dplan; a.tree_pool = c->dtree_pool; a.post_pool = c->dpost_pool; a.prog_pool = c->dprog_pool.p;
-    a.prog_len = c->dprog_len; a.post_stride = c->post_stride;
+    a.compile_scratch = c->dcompile_scratch;
+    a.prog_desc = c->dprog_len; a.post_stride = c->post_stride;
     a.fit = c->dfit[c->cur]; a.index_best = c->dindex_best;
     a.P = c->cfg.population_size; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
     a.max_depth = c->cfg.max_depth_creation; a.zero_depth = c->cfg.zero_depth;
@@ -364,7 +364,9 @@ int stage_programs(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len
     progs.clear();
     stack_need = 0;
     std::string err;
-    std::vector<uint16_t> post, abs_stack;
+    std::vector<uint16_t> post;
+    std::vector<uint32_t> scratch;
+    std::vector<CompileFrame> frames;
     for (int32_t t = 0; t < n; ++t) {
         if (len[t] <= 0 || off[t] < 0) { hoff[t] = 0; hlen[t] = 0; continue; }
         if ((int64_t)off[t] + len[t] > pool_len) return fail(c, "tree %d exceeds the tree pool", t);
@@ -374,12 +376,13 @@ int stage_programs(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len
             return fail(c, "tree %d: %s", t, err.c_str());
         const size_t start = progs.size();
         progs.resize(start + post.size() / 2 + 1);
-        abs_stack.resize((size_t)sp + 1);
+        scratch.resize(post.size());
+        frames.resize(post.size() / 2 + 2);                  // tree depth + 1 <= function nodes + 1
         int n_ins = 0, need = 0;
-        if (!compile_postfix(post.data(), (int)post.size(), progs.data() + start, n_ins, need, abs_stack.data(), (int)abs_stack.size()))
+        if (!compile_postfix(post.data(), (int)post.size(), progs.data() + start, n_ins, need, scratch.data(), frames.data(), (int)frames.size()))
             return fail(c, "tree %d: cannot compile", t);
         progs.resize(start + n_ins);
-        hoff[t] = (int32_t)start; hlen[t] = n_ins;
+        hoff[t] = (int32_t)start; hlen[t] = prog_desc(n_ins, need);
         stack_need = std::max(stack_need, need);
     }
     return 0;
@@ -473,16 +476,13 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         cudaDeviceProp prop{};
         CUC(cudaGetDeviceProperties(&prop, cfg->device));
         c->sm_count = prop.multiProcessorCount;
-        if (const char *e = getenv("GSGP_INTERP_CPT")) c->interp_cpt = (atoi(e) == 2) ? 2 : 4;
-        if (const char *e = getenv("GSGP_INTERP_TILE")) { int t = atoi(e); if (t >= 128 && t <= 2048 && t % 128 == 0) c->interp_tile = t; }
+        if (const char *e = getenv("GSGP_INTERP_TILE")) { int t = atoi(e); if (t >= kPass && t <= 4096 && t % kPass == 0) c->interp_tile = t; }
         const int kMaxSmem = 227 * 1024;
-        CUC(cudaFuncSetAttribute(interp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(interp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(interp_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(interp_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
-    // +64 doubles of slack: the unstaged 4-cases-per-lane path may read (never use) past the last tile
-    CUC(cudaMalloc((void **)&c->dX, sizeof(double) * (row * cfg->nvar + 64)));
+    // +256 doubles of slack: the unstaged multi-pair path may read (never use) past the last tile
+    CUC(cudaMalloc((void **)&c->dX, sizeof(double) * (row * cfg->nvar + 256)));
     CUC(cudaMalloc((void **)&c->dy, sizeof(double) * row));
     CUC(cudaMalloc((void **)&c->dsym, sizeof(double) * (size_t)c->n_symbols));
     CUC(cudaMemsetAsync(c->dX, 0, sizeof(double) * row * cfg->nvar, c->stream));
@@ -514,6 +514,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         c->tree_stride = 4 * (1 << d);                         // ints  <= 4*2^d-3 (main_cpu.go:609-639)
         CUC(cudaMalloc((void **)&c->dtree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
         CUC(cudaMalloc((void **)&c->dpost_pool, sizeof(uint16_t) * 2 * (size_t)P * c->post_stride));
+        CUC(cudaMalloc((void **)&c->dcompile_scratch, sizeof(uint32_t) * 2 * (size_t)P * c->post_stride));
         CUC(c->dprog_pool.reserve((size_t)2 * P * c->prog_stride));
         std::vector<int32_t> off(2 * (size_t)P);
         for (int t = 0; t < 2 * P; ++t) off[t] = t * c->prog_stride;
@@ -559,7 +560,7 @@ void gsgp_destroy(gsgp_ctx *c)
     for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
     cudaFree(c->dplan); cudaFree(c->dtree_pool); cudaFree(c->dprog_off); cudaFree(c->dprog_len);
-    cudaFree(c->dpost_pool); cudaFree(c->dindex_best); cudaFree(c->dhist);
+    cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -756,7 +757,7 @@ int gsgp_run_generations(gsgp_ctx *c, int32_t n)
     if (check_ready(c)) return 1;
     if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_run_generations needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
     if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
-    const int32_t max_sp = std::max(1, c->cfg.max_depth_creation - 1);   // spill levels <= depth of a TT node
+    const int32_t max_sp = std::min(kMaxSmemLevels, c->cfg.max_depth_creation <= 6 ? 2 : 3);   // shared-memory spill levels
     if (ensure_hist(c, c->generation + n)) return 1;
     for (int32_t g = 0; g < n; ++g) {
         if (launch_plan(c, c->generation + 1)) return 1;
