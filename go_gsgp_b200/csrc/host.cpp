@@ -1,6 +1,8 @@
 // host.cpp -- host-side driver pieces of the hot path (include/gsgp_host.h): RNG, constants,
 // initial-population trees and the per-generation plan.  Pure C++, no CUDA.
 #include "../../include/gsgp_host.h"
+#include "program.hpp"
+#include "trees.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -201,6 +203,26 @@ int32_t gsgph_best_individual(const gsgph_params *p, const double *fit)
 
 // strconv.FormatFloat(v, 'g', -1, 64) as fmt's %v prints it: shortest round-trip digits, exponent
 // form when exp < -4 || exp >= 6, at least two exponent digits.
+int gsgph_compile_tree(const int32_t *tree, int32_t len, int32_t n_symbols, uint32_t *code_ab, int32_t cap,
+                       int32_t *n_ins, int32_t *spill_levels)
+{
+    std::vector<uint16_t> post;
+    std::string err;
+    int32_t sp = 0;
+    if (!tree || len <= 0 || !gsgp::prefix_to_postfix(tree, len, n_symbols, post, sp, err)) return 1;
+    std::vector<gsgp::Ins> prog(post.size() / 2 + 1);
+    std::vector<uint32_t> scratch(post.size());
+    std::vector<gsgp::CompileFrame> frames(post.size() / 2 + 2);
+    int n = 0, need = 0;
+    if (!gsgp::compile_postfix(post.data(), (int)post.size(), prog.data(), n, need, scratch.data(), frames.data(), (int)frames.size()))
+        return 2;
+    if (n > cap) return 3;
+    for (int i = 0; i < n; ++i) { code_ab[2 * i] = prog[i].code; code_ab[2 * i + 1] = prog[i].ab; }
+    if (n_ins) *n_ins = n;
+    if (spill_levels) *spill_levels = need;
+    return 0;
+}
+
 int gsgph_format_float(double v, char *buf, int32_t cap)
 {
     if (std::isnan(v)) return snprintf(buf, cap, "NaN");

@@ -32,6 +32,8 @@ HOST_SIGNATURES = {
                                    C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_best_individual": (C.c_int32, [C.POINTER(HostParams), C.POINTER(C.c_double)]),
     "gsgph_format_float": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
+    "gsgph_compile_tree": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int32,
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _bound = False
@@ -52,6 +54,19 @@ def format_float(v: float) -> str:
     buf = C.create_string_buffer(64)
     _lib().gsgph_format_float(float(v), buf, 64)
     return buf.value.decode()
+
+
+def compile_tree(tree, n_symbols):
+    """Reference tree array -> (code[n], ab[n], spill_levels): the program the interpreter kernel runs."""
+    t = np.ascontiguousarray(tree, np.int32)
+    cap = max(1, len(t))
+    out = np.zeros(2 * cap, np.uint32)
+    n, need = C.c_int32(), C.c_int32()
+    rc = _lib().gsgph_compile_tree(capi.iptr(t), len(t), n_symbols, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap,
+                                   C.byref(n), C.byref(need))
+    if rc:
+        raise ValueError(f"malformed tree (gsgph_compile_tree rc={rc})")
+    return out[0:2 * n.value:2].copy(), out[1:2 * n.value:2].copy(), need.value
 
 
 class HostDriver:

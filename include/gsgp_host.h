@@ -50,6 +50,14 @@ int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int
 
 int32_t gsgph_best_individual(const gsgph_params *p, const double *fit);     /* :1180-1188 */
 
+/* The interpreter's program for one tree (csrc/program.hpp), as the shim builds it before upload:
+ * pointer-prefix array (main_cpu.go:609-639 format) -> validated postfix -> accumulator program.
+ * code_ab receives 2 uint32 per instruction {level<<8 | flags | aop, a | b<<16}; returns non-zero on a
+ * malformed tree or when cap (instructions) is too small.  No CUDA involved: lets hosts and CPU tests inspect
+ * exactly what the device will run. */
+int gsgph_compile_tree(const int32_t *tree, int32_t len, int32_t n_symbols, uint32_t *code_ab, int32_t cap,
+                       int32_t *n_ins, int32_t *spill_levels);
+
 /* Go fmt %v of a float64 (fitness / semantic output lines, main_cpu.go:123-126,1405-1409) */
 int gsgph_format_float(double v, char *buf, int32_t cap);
 

@@ -1,0 +1,77 @@
+"""Run under torchrun (one rank per GPU): case-sharded engines in lock-step with the (global) oracle.
+Every rank passes the same dataset / plan / trees; each keeps its shard; fitness must come back
+bit-identical on every rank and within 1e-9 of the oracle; the local semantic shards must match."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import binding as ob                      # noqa: E402
+from go_gsgp_b200 import Engine, capi                 # noqa: E402
+from tests.util import synth_dataset, rel_err         # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    for rng_kind, mode in ((ob.RNG_ALFG, capi.RNG_HOST_REPLAY), (ob.RNG_PHILOX, capi.RNG_DEVICE_PHILOX)):
+        X, y, nrow = synth_dataset(2, 20_003, 7, nrow=15_001)          # ragged: shards of unequal size
+        N, V = X.shape
+        P = 64
+        cfg = ob.make_config(population_size=P, rng_kind=rng_kind, rng_seed=5, error_measure=ob.RMSE)
+        o = ob.Oracle(cfg, X, y, nrow)
+        o.create_T_F()
+        e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE, rng_seed=5,
+                   rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=nccl_id)
+        e.set_dataset(X, y)
+        e.set_constants(o.symbol_values())
+        o.initialize_population(0)
+        e.eval_initial(0, [o.initial_tree(i) for i in range(P)])
+        o.evaluate()
+        fit, fit_test, best = e.fitness_all()
+        assert best == o.index_best and np.all(rel_err(fit, o.fit()) <= 1e-9)
+        tr_lo, tr_hi = Engine.shard_range(nrow, rank, world)
+        te_lo, te_hi = Engine.shard_range(N - nrow, rank, world)
+        for g in range(6):
+            o.generation()
+            if mode == capi.RNG_HOST_REPLAY:
+                fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
+            else:
+                e.run_generations(1)
+                fit, fit_test, best = e.get_fitness()
+                plan = e.get_plan()
+                ref = o.last_plan()
+                for f in ("op", "elite", "p1", "p2"):
+                    live = ref["elite"] == 0 if f in ("p1", "p2") else slice(None)
+                    assert np.array_equal(plan[f][live], ref[f][live]), (rank, g, f)
+            assert best == o.index_best, (rank, g, best, o.index_best)
+            assert np.all(rel_err(fit, o.fit()) <= 1e-9) and np.all(rel_err(fit_test, o.fit_test()) <= 1e-9)
+            allfit = [torch.zeros(P, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(allfit, torch.from_numpy(fit).cuda())
+            for t in allfit:                                              # bit-identical on every rank
+                assert torch.equal(t.view(torch.int64), allfit[0].view(torch.int64))
+        sem = e.get_semantics()
+        ref = o.semantics()
+        ref_local = np.concatenate([ref[:, tr_lo:tr_hi], ref[:, nrow + te_lo:nrow + te_hi]], axis=1)
+        assert sem.shape == ref_local.shape and np.all(rel_err(sem, ref_local) <= 1e-9)
+        e.close(); o.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIGPU_OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,8 @@ Bars: tree semantics bit-exact (IEEE + - * / without con
 GS-operator semantics and fitness within 1e-9 relative in fp64; parent indices, tree choices and
 the best index exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -316,3 +318,19 @@ def test_error_behaviour():
             e.generation(plan, np.zeros(1, np.int32))               # parent out of range
         with pytest.raises(g.GsgpError):
             e.run_generations(1)                                    # replay-mode context
+
+
+@pytest.mark.gpu
+def test_multi_gpu_case_sharding_matches_oracle():
+    """N>1: case-sharded engines (NCCL all-gather of the partial sums) against the global oracle."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs on the box")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(os.path.dirname(__file__), "multigpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
