@@ -190,13 +190,15 @@ def main():
     nrow, nrow_test = int(0.8 * n_global), n_global - int(0.8 * n_global)
     X, y = synth(w["cfg_id"], n_global, V)
 
-    nccl_id = None
-    if world > 1:
+    def fresh_nccl_id():
+        """an ncclUniqueId serves one communicator: rank 0 draws a new one per context, broadcast to all"""
+        if world == 1:
+            return None
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
 
     def barrier():
         if dist is not None:
@@ -212,14 +214,14 @@ def main():
 
     common = dict(population_size=P, nvar=V, nrow=nrow, nrow_test=nrow_test, max_depth_creation=w["depth"],
                   error_measure=capi.RMSE, p_crossover=w["p_xo"], p_mutation=w["p_mut"], rng_seed=1,
-                  device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id)
+                  device=local_rank, rank=rank, world_size=world)
     host = HostDriver(population_size=P, nvar=V, max_depth_creation=w["depth"], p_crossover=w["p_xo"],
                       p_mutation=w["p_mut"], seed=1)
     sym = host.create_T_F()
     init_trees = host.initialize_population(0)
 
     def setup(rng_mode):
-        e = Engine(rng_mode=rng_mode, **common)
+        e = Engine(rng_mode=rng_mode, nccl_id=fresh_nccl_id(), **common)
         e.set_dataset(X, y)
         e.set_constants(sym)
         e.eval_initial(0, init_trees)

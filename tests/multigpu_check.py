@@ -20,11 +20,13 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        buf.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(buf, 0)
-    nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    def fresh_nccl_id():                                   # an ncclUniqueId serves ONE communicator
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
 
     for rng_kind, mode in ((ob.RNG_ALFG, capi.RNG_HOST_REPLAY), (ob.RNG_PHILOX, capi.RNG_DEVICE_PHILOX)):
         X, y, nrow = synth_dataset(2, 20_003, 7, nrow=15_001)          # ragged: shards of unequal size
@@ -34,7 +36,7 @@ def main():
         o = ob.Oracle(cfg, X, y, nrow)
         o.create_T_F()
         e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE, rng_seed=5,
-                   rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=nccl_id)
+                   rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=fresh_nccl_id())
         e.set_dataset(X, y)
         e.set_constants(o.symbol_values())
         o.initialize_population(0)
