@@ -334,3 +334,51 @@ def test_multi_gpu_case_sharding_matches_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(os.path.dirname(__file__), "multigpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_sigmoid_accuracy_scan():
+    """sigma(R) = 1/(1+exp64(-R)) over a dense scan of R, isolated through a crossover whose parents are the
+    constant vectors 1 and 0 (child = 1*s + 0*(1-s) = s exactly).  The fast path must stay within 4 * 2^-52
+    relative of the oracle (libm exp + IEEE divide); the quirk bands must be exact."""
+    g = _engine_mod()
+    rng = np.random.default_rng(3)
+    n = 1 << 16
+    scan = np.concatenate([
+        rng.uniform(-40, 40, n // 4), rng.uniform(-700.5, 700.5, n // 4), rng.uniform(-1e-3, 1e-3, n // 8),
+        np.ldexp(rng.uniform(1, 2, n // 8), rng.integers(-60, -20, n // 8)) * rng.choice([-1, 1], n // 8),
+        rng.uniform(699, 760, n // 8), -rng.uniform(699, 760, n // 16),
+        np.array([0.0, -0.0, 2.0 ** -28, -(2.0 ** -28), np.nextafter(2.0 ** -28, 0), 700.0, -700.0, np.nextafter(700.0, 800),
+                  709.78, 709.79, -745.13, -745.14, np.inf, -np.inf, np.nan, 1e-300, -1e-300, 5e-324])])
+    N = len(scan)
+    X = np.stack([scan, np.zeros(N)], axis=1)
+    y = np.zeros(N)
+    nrow = N - 1000
+    P = 4
+    cfg = ob.make_config(population_size=P, error_measure=ob.MSE)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    e = g.Engine(population_size=P, nvar=2, nrow=nrow, nrow_test=N - nrow, error_measure=ob.MSE)
+    e.set_dataset(X, y)
+    e.set_constants(o.symbol_values())
+    seeds = [np.ones(N), np.zeros(N), np.full(N, 0.25), np.full(N, -3.0)]
+    for i, s in enumerate(seeds):
+        o.seed_semantic(i, s); e.seed_semantic(i, s)
+    o.initialize_population(P); o.evaluate(); e.fitness_all()
+    plan = np.zeros(P, ob.PLAN_DTYPE)
+    pool = np.array([4, 4, 5], np.int32)                         # trees: x0 ; x0 ; x1 (== 0)
+    plan[0] = (ob.OP_XO, 0, 0, 1, 0, 1, -1, 0, 0.0)              # child = sigma(x0)
+    plan[1] = (ob.OP_MUT, 0, 1, 0, 1, 1, 2, 1, 1.0)              # child = 0 + 1*(sigma(x0) - sigma(0))
+    plan[2] = (ob.OP_XO, 0, 2, 3, 0, 1, -1, 0, 0.0)
+    plan[3] = (ob.OP_REPR, 0, 0, 0, -1, 0, -1, 0, 0.0)
+    o.generation_replay(plan, pool)
+    e.generation(plan, pool)
+    got, want = e.get_semantics(), o.semantics()
+    err = rel_err(got[0], want[0])
+    assert np.nanmax(err) <= 4 * 2.0 ** -52, (np.nanmax(err), scan[np.nanargmax(err)])
+    # where exp64's rules (not exp's last bit) decide the value, the result is bit-identical:
+    # sigma in {0.5, 1} below 2^-28, 1/(1+MaxFloat64) past the overflow, exactly 1 once exp(-R) < 2^-53
+    decided = (np.abs(scan) < 2.0 ** -28) | (scan < -709.79) | (scan > 40) | ~np.isfinite(scan)
+    np.testing.assert_array_equal(got[0][decided], want[0][decided])
+    assert_close(got[1], want[1], 1e-12, "mutation delta")             # difference of two sigmoids (cancellation)
+    assert_close(got[2], want[2], TOL, "crossover")
+    e.close(); o.close()
