@@ -191,7 +191,7 @@ InterpGeom interp_geometry(const gsgp_ctx *c, int32_t n_slots, int32_t levels)
     const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
     g.tile = 256; g.stage = false;
     for (int32_t t : {c->interp_tile, 256}) {
-        if (ncol * t * sizeof(double) + spill + fixed <= (size_t)96 * 1024) { g.tile = t; g.stage = true; break; }
+        if (ncol * t * sizeof(double) + spill + fixed <= (size_t)112 * 1024) { g.tile = t; g.stage = true; break; }
     }
     const int32_t n_tiles = (c->L.n_pad + g.tile - 1) / g.tile;
     const int32_t target = c->sm_count * 8;
