@@ -282,21 +282,29 @@ def main():
     e.close()
     clocks = sampler.stop()
 
-    # ---- roofline of the dominant kernel (GS operators + fitness) ----------------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = measured_peak()
     n_gs, ms_gs, _ = prof[capi.K_GSOP]
     n_it, ms_it, _ = prof[capi.K_INTERP]
     local_updates = float(P) * float(n_local)
-    gs_bytes_per_gen = local_updates * (32.0 * frac_computed + 16.0 * (1.0 - frac_computed))
-    gens_recorded = max(1, K)
-    achieved = gs_bytes_per_gen * gens_recorded / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
-    roofline = {"bound": "hbm", "kernel": "gsop_kernel (GS crossover/mutation/reproduction + error reduction)",
+    frac_xo = float(np.mean(computed & (plan["op"] == capi.OP_XO)))
+    frac_mut = float(np.mean(computed & (plan["op"] == capi.OP_MUT)))
+    fused = n_it == 0
+    if fused:
+        # gen_kernel: interpreter + GS operators + error sums in one launch, R stays on chip:
+        # XO reads p1, p2 and writes the child (24 B); MUT reads the parent and writes the child (16 B); copy 16 B
+        bpu = 24.0 * frac_xo + 16.0 * frac_mut + 16.0 * (1.0 - frac_xo - frac_mut)
+        kname = "gen_kernel (tree interpreter + GS crossover/mutation/reproduction + error reduction, fused)"
+    else:
+        bpu = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
+        kname = "gsop_kernel (GS crossover/mutation/reproduction + error reduction)"
+    achieved = local_updates * bpu * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": peak_src,
-                "bytes_per_update": 32.0 * frac_computed + 16.0 * (1.0 - frac_computed),
-                "launches": n_gs, "ms_total": ms_gs,
+                "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
+                "launches": n_gs, "ms_total": ms_gs, "pipeline": "fused" if fused else "unfused",
                 "interp_kernel": {"launches": n_it, "ms_total": ms_it},
-                "share_of_step": {"gsop": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None}}
+                "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None}}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

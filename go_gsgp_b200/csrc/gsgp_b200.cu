@@ -99,7 +99,10 @@ struct gsgp_ctx {
     Layout L{};
     int32_t tr_lo = 0, tr_hi = 0, te_lo = 0, te_hi = 0;     // global row ranges of this shard
     int32_t n_symbols = 0;
-    int32_t n_tiles = 0;
+    int32_t n_tiles = 0;                                      // 2048-case tiles of gsop_kernel
+    int32_t n_tiles_gen = 0;                                  // 256-case tiles of gen_kernel
+    bool fused = false;                                       // generation = one gen_kernel launch per chunk
+    int32_t gen_levels = 2;
     int32_t chunk_inds = 0;                                   // individuals per interp+gsop launch pair
     int32_t tree_stride = 0, prog_stride = 0;
     int32_t generation = 0;
@@ -248,12 +251,49 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     return 0;
 }
 
+// fused pipeline: shared memory of one gen_kernel block for `ipg` individuals per group
+size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg)
+{
+    const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
+    const size_t per_warp = ((size_t)(levels + 2) * kPass + 2 * 2 * kProgSmem) * sizeof(double);
+    return (ncol + 1) * kPass * sizeof(double) + per_warp * kGenWarps + (size_t)ipg * sizeof(GenSlot) +
+           (1 + kGenWarps) * sizeof(uint64_t) + 16;
+}
+
+int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const double *sem_old, double *sem_new, double bytes)
+{
+    if (nk <= 0) return 0;
+    const int32_t n_tiles = c->n_tiles_gen;
+    const int32_t target = c->sm_count * 8;
+    int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
+    groups = std::min(groups, std::max(1, (nk + 31) / 32));
+    int32_t ipg = (nk + groups - 1) / groups;
+    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
+    groups = (nk + ipg - 1) / ipg;
+    if (groups > 65535) return fail(c, "population chunk too large for one launch");
+    GenArgs a{};
+    a.plan = c->dplan; a.prog_pool = c->dprog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->dprog_len;
+    a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
+    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->L.n_pad; a.partial = c->dpartial;
+    a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = n_tiles; a.smem_levels = c->gen_levels; a.L = c->L;
+    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg);
+    dim3 grid(n_tiles, groups);
+    ProfScope ps(c, GSGP_K_GSOP, bytes);
+    switch (c->cfg.error_measure) {
+    case GSGP_MAE: gen_kernel<GSGP_MAE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
+    case GSGP_MRE: gen_kernel<GSGP_MRE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
+    default:       gen_kernel<GSGP_MSE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
+    }
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
 // local partials -> (all-gather across ranks) -> fitness -> best-of-generation
-int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf)
+int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_tiles)
 {
     const int P = c->cfg.population_size;
     {
-        ReduceArgs r{c->dplan, c->dpartial, c->dsums, P, c->n_tiles, mode};
+        ReduceArgs r{c->dplan, c->dpartial, c->dsums, P, n_tiles, mode};
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
         reduce_partials_kernel<<<(P * 32 + 255) / 256, 256, 0, c->stream>>>(r);
         CU(c, cudaGetLastError());
@@ -320,17 +360,28 @@ int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may 
     const double n_cases = (double)(c->L.n_tr + c->L.n_te);
     for (int32_t k0 = 0; k0 < P; k0 += c->chunk_inds) {
         const int32_t nk = std::min(c->chunk_inds, P - k0);
-        double n_trees = 1.2 * nk, bytes = 30.4 * nk * n_cases;       // expected mix when the plan lives on the device
+        double n_trees = 1.2 * nk, frac_xo = 0.6, frac_mut = 0.3;     // expected mix when the plan lives on the device
         if (host_plan) {
-            n_trees = 0;
-            for (int32_t k = k0; k < k0 + nk; ++k) n_trees += (host_plan[k].tree0_len > 0) + (host_plan[k].tree1_len > 0);
-            bytes = gs_bytes(host_plan, k0, nk, n_cases);
+            n_trees = 0; double nx = 0, nm = 0;
+            for (int32_t k = k0; k < k0 + nk; ++k) {
+                n_trees += (host_plan[k].tree0_len > 0) + (host_plan[k].tree1_len > 0);
+                const bool computed = !host_plan[k].elite && host_plan[k].op != GSGP_OP_REPR;
+                nx += computed && host_plan[k].op == GSGP_OP_XO; nm += computed && host_plan[k].op == GSGP_OP_MUT;
+            }
+            frac_xo = nx / nk; frac_mut = nm / nk;
         }
-        if (launch_interp(c, c->dprog_pool.p, c->dprog_off, c->dprog_len, 2 * k0, 2 * nk, max_sp, c->dR,
-                          c->L.n_pad, n_trees)) return 1;
-        if (launch_gsop(c, GS_MODE_GENERATION, k0, nk, k0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
+        if (c->fused) {
+            // algorithmic bytes of the fused launch: XO 24 B (p1, p2, child), MUT 16 B (parent, child), copy 16 B
+            const double bytes = (24.0 * frac_xo + 16.0 * frac_mut + 16.0 * (1.0 - frac_xo - frac_mut)) * nk * n_cases;
+            if (launch_gen(c, k0, nk, 0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
+        } else {
+            const double bytes = (32.0 * (frac_xo + frac_mut) + 16.0 * (1.0 - frac_xo - frac_mut)) * nk * n_cases;
+            if (launch_interp(c, c->dprog_pool.p, c->dprog_off, c->dprog_len, 2 * k0, 2 * nk, max_sp, c->dR,
+                              c->L.n_pad, n_trees)) return 1;
+            if (launch_gsop(c, GS_MODE_GENERATION, k0, nk, k0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
+        }
     }
-    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf)) return 1;
+    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, c->fused ? c->n_tiles_gen : c->n_tiles)) return 1;
     c->cur = new_buf;                                                  // update_tables main_cpu.go:1191-1197
     c->generation++;
     if (launch_best(c, c->cur, c->generation)) return 1;               // :1492
@@ -468,6 +519,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     c->L.n_pad = c->L.tr_pad + round_up(c->L.n_te, 16);
     if (c->L.n_pad == 0) c->L.n_pad = 16;
     c->n_tiles = (c->L.n_pad + kGsTile - 1) / kGsTile;
+    c->n_tiles_gen = (c->L.n_pad + kPass - 1) / kPass;
     c->n_symbols = 4 + cfg->nvar + cfg->num_constants;
 
     const int P = cfg->population_size;
@@ -480,6 +532,15 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         const int kMaxSmem = 227 * 1024;
         CUC(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        // pipeline: fused (one gen_kernel launch per generation, R stays on chip) unless the dataset's columns
+        // do not fit shared memory, the caller wants R kept (proto dump), or GSGP_PIPELINE=unfused
+        const char *pl = getenv("GSGP_PIPELINE");
+        c->gen_levels = 2;
+        c->fused = !(cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) && !(pl && strcmp(pl, "unfused") == 0) &&
+                   gen_smem_bytes(c, c->gen_levels, 32) <= (size_t)kMaxSmem;
     }
     // +256 doubles of slack: the unstaged multi-pair path may read (never use) past the last tile
     CUC(cudaMalloc((void **)&c->dX, sizeof(double) * (row * cfg->nvar + 256)));
@@ -496,7 +557,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * P, c->stream));
         CUC(cudaMemsetAsync(c->dfit_test[b], 0, sizeof(double) * P, c->stream));
     }
-    CUC(cudaMalloc((void **)&c->dpartial, sizeof(double) * 2 * (size_t)P * c->n_tiles));
+    CUC(cudaMalloc((void **)&c->dpartial, sizeof(double) * 2 * (size_t)P * std::max(c->n_tiles, c->n_tiles_gen)));
     CUC(cudaMalloc((void **)&c->dsums, sizeof(double) * 2 * P));
     CUC(cudaMalloc((void **)&c->dsums_all, sizeof(double) * 2 * P * (size_t)cfg->world_size));
     CUC(cudaMalloc((void **)&c->dplan, sizeof(gsgp_plan_entry) * P));
@@ -531,8 +592,9 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     if (cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) budget = pair * P;
     size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)P, budget / pair));
     chunk = std::min<size_t>(chunk, 65535);
+    if (c->fused) chunk = 1;                                          // R never leaves the SM: no workspace
     if (chunk * pair > free_b) { fail(c, "not enough device memory for the tree-semantic workspace"); return bail(); }
-    c->chunk_inds = (int32_t)chunk;
+    c->chunk_inds = c->fused ? P : (int32_t)chunk;
     CUC(cudaMalloc((void **)&c->dR, chunk * pair));
     CUC(cudaMemsetAsync(c->dR, 0, chunk * pair, c->stream));
 
@@ -708,7 +770,7 @@ int gsgp_fitness_all(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_
         const int32_t nk = std::min(65535, P - k0);
         if (launch_gsop(c, GS_MODE_FITNESS_ONLY, k0, nk, 0, c->dsem[c->cur], c->dsem[c->cur], 8.0 * nk * n_cases)) return 1;
     }
-    if (launch_finalize(c, GS_MODE_FITNESS_ONLY, c->cur, c->cur)) return 1;
+    if (launch_finalize(c, GS_MODE_FITNESS_ONLY, c->cur, c->cur, c->n_tiles)) return 1;
     if (launch_best(c, c->cur, c->generation)) return 1;
     c->fitness_valid = true;
     return read_fitness(c, fit, fit_test, index_best);
