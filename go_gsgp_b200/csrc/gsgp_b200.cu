@@ -115,11 +115,22 @@ struct gsgp_ctx {
     double *dR = nullptr;
     double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
     gsgp_plan_entry *dplan = nullptr;
-    int32_t *dtree_pool = nullptr;                            // device mode
-    DevBuf<Ins> dprog_pool;                                   // accumulator programs (program.hpp)
-    uint16_t *dpost_pool = nullptr;                           // device mode: postfix scratch of plan_kernel
+    // random trees + programs of a generation.  Host replay uses set 0; device mode alternates between two
+    // sets so that plan_draw_kernel for generation g+1 (second stream) overlaps generation g's arithmetic.
+    struct DrawSet {
+        int32_t *tree_pool = nullptr;                         // device mode: reference arrays (gsgp_get_tree)
+        DevBuf<Ins> prog_pool;                                // accumulator programs (program.hpp)
+        int32_t *prog_desc = nullptr;                         // [2P] prog_desc(n, need)
+        DrawRec *rec = nullptr;                               // device mode: what plan_draw_kernel drew
+        int32_t *cand = nullptr;                              // device mode: tournament candidates
+    } ds[2];
+    int dcur = 0;                                             // set of the current / last generation
+    int32_t drawn_gen = -1;                                   // generation whose draws sit in ds[drawn_gen & 1]
+    cudaStream_t stream2 = nullptr;                           // plan_draw_kernel
+    cudaEvent_t ev_draw[2] = {nullptr, nullptr}, ev_free = nullptr;
+    uint16_t *dpost_pool = nullptr;                           // device mode: postfix scratch of plan_draw_kernel
     uint32_t *dcompile_scratch = nullptr;                     // device mode: program-builder scratch
-    int32_t *dprog_off = nullptr, *dprog_len = nullptr;
+    int32_t *dprog_off = nullptr;
     int32_t post_stride = 0;
     int32_t interp_tile = 256;                                // tunable (GSGP_INTERP_TILE)
     int sm_count = 148;
@@ -160,8 +171,8 @@ int fail(gsgp_ctx *c, const char *fmt, ...)
 inline int32_t round_up(int32_t x, int32_t m) { return (x + m - 1) / m * m; }
 
 struct ProfScope {                 // CUDA-event bracket around one kernel launch on ctx->stream
-    gsgp_ctx *c; int k; bool rec = false; size_t idx = 0;
-    ProfScope(gsgp_ctx *c_, int k_, double bytes) : c(c_), k(k_)
+    gsgp_ctx *c; int k; bool rec = false; size_t idx = 0; cudaStream_t st;
+    ProfScope(gsgp_ctx *c_, int k_, double bytes, cudaStream_t st_ = nullptr) : c(c_), k(k_), st(st_ ? st_ : c_->stream)
     {
         c->launch_count++;
         ProfSlot &s = c->prof[k];
@@ -174,9 +185,9 @@ struct ProfScope {                 // CUDA-event bracket around one kernel launc
             s.ev.push_back({a, b});
         }
         idx = s.used++; rec = true; s.bytes += bytes;
-        cudaEventRecord(s.ev[idx].first, c->stream);
+        cudaEventRecord(s.ev[idx].first, st);
     }
-    ~ProfScope() { if (rec) cudaEventRecord(c->prof[k].ev[idx].second, c->stream); }
+    ~ProfScope() { if (rec) cudaEventRecord(c->prof[k].ev[idx].second, st); }
 };
 
 // ---- launches ---------------------------------------------------------------------------------
@@ -272,7 +283,7 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
     groups = (nk + ipg - 1) / ipg;
     if (groups > 65535) return fail(c, "population chunk too large for one launch");
     GenArgs a{};
-    a.plan = c->dplan; a.prog_pool = c->dprog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->dprog_len;
+    a.plan = c->dplan; a.prog_pool = c->ds[c->dcur].prog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->ds[c->dcur].prog_desc;
     a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
     a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->L.n_pad; a.partial = c->dpartial;
     a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = n_tiles; a.smem_levels = c->gen_levels; a.L = c->L;
@@ -341,17 +352,6 @@ int launch_best(gsgp_ctx *c, int buf, int32_t gen)
     return 0;
 }
 
-// algorithmic bytes of the GS-operator launches: XO / MUT 32 B, copy 16 B per update
-double gs_bytes(const gsgp_plan_entry *plan, int32_t k0, int32_t nk, double n_cases)
-{
-    double b = 0.0;
-    for (int32_t k = k0; k < k0 + nk; ++k) {
-        const bool computed = !plan[k].elite && (plan[k].op == GSGP_OP_XO || plan[k].op == GSGP_OP_MUT);
-        b += (computed ? 32.0 : 16.0) * n_cases;
-    }
-    return b;
-}
-
 // the interp -> gsop pipeline of one generation, chunked so that R fits its workspace
 int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may be NULL */, int32_t max_sp)
 {
@@ -376,7 +376,7 @@ int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may 
             if (launch_gen(c, k0, nk, 0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
         } else {
             const double bytes = (32.0 * (frac_xo + frac_mut) + 16.0 * (1.0 - frac_xo - frac_mut)) * nk * n_cases;
-            if (launch_interp(c, c->dprog_pool.p, c->dprog_off, c->dprog_len, 2 * k0, 2 * nk, max_sp, c->dR,
+            if (launch_interp(c, c->ds[c->dcur].prog_pool.p, c->dprog_off, c->ds[c->dcur].prog_desc, 2 * k0, 2 * nk, max_sp, c->dR,
                               c->L.n_pad, n_trees)) return 1;
             if (launch_gsop(c, GS_MODE_GENERATION, k0, nk, k0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
         }
@@ -389,12 +389,13 @@ int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may 
     return 0;
 }
 
-int launch_plan(gsgp_ctx *c, int32_t generation)
+PlanArgs plan_args(gsgp_ctx *c, int32_t generation)
 {
+    gsgp_ctx::DrawSet &d = c->ds[generation & 1];
     PlanArgs a{};
-    a.plan = c->dplan; a.tree_pool = c->dtree_pool; a.post_pool = c->dpost_pool; a.prog_pool = c->dprog_pool.p;
-    a.compile_scratch = c->dcompile_scratch;
-    a.prog_desc = c->dprog_len; a.post_stride = c->post_stride;
+    a.plan = c->dplan; a.rec = d.rec; a.cand = d.cand; a.tree_pool = d.tree_pool; a.post_pool = c->dpost_pool;
+    a.compile_scratch = c->dcompile_scratch; a.prog_pool = d.prog_pool.p; a.prog_desc = d.prog_desc;
+    a.post_stride = c->post_stride;
     a.fit = c->dfit[c->cur]; a.index_best = c->dindex_best;
     a.P = c->cfg.population_size; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
     a.max_depth = c->cfg.max_depth_creation; a.zero_depth = c->cfg.zero_depth;
@@ -402,8 +403,33 @@ int launch_plan(gsgp_ctx *c, int32_t generation)
     a.tree_stride = c->tree_stride; a.prog_stride = c->prog_stride;
     a.generation = generation; a.p_xo = c->cfg.p_crossover; a.p_mut = c->cfg.p_mutation;
     a.seed = c->cfg.rng_seed;
+    return a;
+}
+
+// everything of generation `generation` that consumes random numbers, on the second stream; it may only
+// overwrite its draw set once the generation that last used it (generation - 2) is done: ev_free
+int launch_draw(gsgp_ctx *c, int32_t generation)
+{
+    const PlanArgs a = plan_args(c, generation);
+    CU(c, cudaStreamWaitEvent(c->stream2, c->ev_free, 0));
+    {
+        ProfScope ps(c, GSGP_K_PLAN, 0.0, c->stream2);
+        plan_draw_kernel<<<(a.P + 127) / 128, 128, 0, c->stream2>>>(a);
+        CU(c, cudaGetLastError());
+    }
+    CU(c, cudaEventRecord(c->ev_draw[generation & 1], c->stream2));
+    c->drawn_gen = generation;
+    return 0;
+}
+
+// tournament winners + elite rule for `generation` on the main stream (needs the previous generation's fit[])
+int launch_select(gsgp_ctx *c, int32_t generation)
+{
+    const PlanArgs a = plan_args(c, generation);
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[generation & 1], 0));
+    c->dcur = generation & 1;
     ProfScope ps(c, GSGP_K_PLAN, 0.0);
-    plan_kernel<<<(a.P + 127) / 128, 128, 0, c->stream>>>(a);
+    plan_select_kernel<<<(a.P + 255) / 256, 256, 0, c->stream>>>(a);
     CU(c, cudaGetLastError());
     return 0;
 }
@@ -563,8 +589,11 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMalloc((void **)&c->dplan, sizeof(gsgp_plan_entry) * P));
     CUC(cudaMemsetAsync(c->dplan, 0, sizeof(gsgp_plan_entry) * P, c->stream));
     CUC(cudaMalloc((void **)&c->dprog_off, sizeof(int32_t) * 2 * P));
-    CUC(cudaMalloc((void **)&c->dprog_len, sizeof(int32_t) * 2 * P));
-    CUC(cudaMemsetAsync(c->dprog_len, 0, sizeof(int32_t) * 2 * P, c->stream));
+    const int n_sets = cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX ? 2 : 1;
+    for (int i = 0; i < n_sets; ++i) {
+        CUC(cudaMalloc((void **)&c->ds[i].prog_desc, sizeof(int32_t) * 2 * P));
+        CUC(cudaMemsetAsync(c->ds[i].prog_desc, 0, sizeof(int32_t) * 2 * P, c->stream));
+    }
     CUC(cudaMalloc((void **)&c->dindex_best, sizeof(int32_t)));
     CUC(cudaMemsetAsync(c->dindex_best, 0, sizeof(int32_t), c->stream));
 
@@ -573,10 +602,18 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         c->post_stride = (1 << (d + 1));                       // nodes <= 2^(d+1)-1
         c->prog_stride = (1 << d);                             // function nodes <= 2^d-1
         c->tree_stride = 4 * (1 << d);                         // ints  <= 4*2^d-3 (main_cpu.go:609-639)
-        CUC(cudaMalloc((void **)&c->dtree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
+        for (int i = 0; i < 2; ++i) {
+            CUC(cudaMalloc((void **)&c->ds[i].tree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
+            CUC(c->ds[i].prog_pool.reserve((size_t)2 * P * c->prog_stride));
+            CUC(cudaMalloc((void **)&c->ds[i].rec, sizeof(DrawRec) * (size_t)P));
+            CUC(cudaMalloc((void **)&c->ds[i].cand, sizeof(int32_t) * 2 * (size_t)P * cfg->tournament_size));
+        }
         CUC(cudaMalloc((void **)&c->dpost_pool, sizeof(uint16_t) * 2 * (size_t)P * c->post_stride));
         CUC(cudaMalloc((void **)&c->dcompile_scratch, sizeof(uint32_t) * 2 * (size_t)P * c->post_stride));
-        CUC(c->dprog_pool.reserve((size_t)2 * P * c->prog_stride));
+        CUC(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_draw[i], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
+        CUC(cudaEventRecord(c->ev_free, c->stream));
         std::vector<int32_t> off(2 * (size_t)P);
         for (int t = 0; t < 2 * P; ++t) off[t] = t * c->prog_stride;
         CUC(cudaMemcpyAsync(c->dprog_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, c->stream));
@@ -621,7 +658,14 @@ void gsgp_destroy(gsgp_ctx *c)
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dsym);
     for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
-    cudaFree(c->dplan); cudaFree(c->dtree_pool); cudaFree(c->dprog_off); cudaFree(c->dprog_len);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->ds[i].tree_pool); cudaFree(c->ds[i].prog_desc); cudaFree(c->ds[i].rec); cudaFree(c->ds[i].cand);
+        if (c->ev_draw[i]) cudaEventDestroy(c->ev_draw[i]);
+    }
+    if (c->ev_free) cudaEventDestroy(c->ev_free);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    cudaFree(c->dplan); cudaFree(c->dprog_off);
     cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -803,11 +847,12 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
     if (stage_programs(c, 2 * P, tree_pool, pool_len, off.data(), len.data(), progs, c->hoff.p, c->hlen.p, max_sp)) return 1;
     CU(c, c->hprog.reserve(progs.size()));
     memcpy(c->hprog.p, progs.data(), sizeof(Ins) * progs.size());
-    CU(c, c->dprog_pool.reserve(progs.size()));
+    c->dcur = 0;
+    CU(c, c->ds[0].prog_pool.reserve(progs.size()));
     CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->dprog_pool.p, c->hprog.p, sizeof(Ins) * progs.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->ds[0].prog_pool.p, c->hprog.p, sizeof(Ins) * progs.size(), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->dprog_off, c->hoff.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->dprog_len, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->ds[0].prog_desc, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
     if (run_generation_kernels(c, c->hplan.p, max_sp)) return 1;
     c->last_plan.assign(plan, plan + P);
     c->last_pool.assign(tree_pool, tree_pool + std::max(pool_len, 0));
@@ -821,8 +866,14 @@ int gsgp_run_generations(gsgp_ctx *c, int32_t n)
     if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
     const int32_t max_sp = std::min(kMaxSmemLevels, c->cfg.max_depth_creation <= 6 ? 2 : 3);   // shared-memory spill levels
     if (ensure_hist(c, c->generation + n)) return 1;
-    for (int32_t g = 0; g < n; ++g) {
-        if (launch_plan(c, c->generation + 1)) return 1;
+    for (int32_t i = 0; i < n; ++i) {
+        const int32_t g = c->generation + 1;
+        if (c->drawn_gen != g && launch_draw(c, g)) return 1;         // (first call / after gsgp_draw_plan)
+        if (launch_select(c, g)) return 1;
+        // generation g-1 and the selection of g are queued: set (g+1)&1 is free once they are done; the draws
+        // of g+1 then run on the second stream under generation g's arithmetic
+        CU(c, cudaEventRecord(c->ev_free, c->stream));
+        if (launch_draw(c, g + 1)) return 1;
         if (run_generation_kernels(c, nullptr, max_sp)) return 1;
     }
     c->last_plan.clear();
@@ -834,6 +885,7 @@ int gsgp_sync(gsgp_ctx *c)
     if (!c) return fail(nullptr, "null context");
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->stream2) CU(c, cudaStreamSynchronize(c->stream2));
     return 0;
 }
 
@@ -891,7 +943,7 @@ int gsgp_get_tree(gsgp_ctx *c, int32_t ind, int32_t which, int32_t *out, int32_t
     if (n <= 0) return 0;
     if (n > cap) return fail(c, "tree buffer too small (%d > %d)", n, cap);
     if (!c->last_plan.empty()) { memcpy(out, c->last_pool.data() + off, sizeof(int32_t) * n); return 0; }
-    CU(c, cudaMemcpyAsync(out, c->dtree_pool + off, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(out, c->ds[c->dcur].tree_pool + off, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -929,7 +981,10 @@ int gsgp_draw_plan(gsgp_ctx *c, int32_t generation, gsgp_plan_entry *plan_out)
 {
     if (check_ready(c)) return 1;
     if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_draw_plan needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
-    if (launch_plan(c, generation)) return 1;
+    CU(c, cudaEventRecord(c->ev_free, c->stream));
+    if (launch_draw(c, generation)) return 1;
+    if (launch_select(c, generation)) return 1;
+    c->drawn_gen = -1;                                                 // a later run re-draws its own generation
     c->last_plan.clear();
     CU(c, cudaMemcpyAsync(plan_out, c->dplan, sizeof(gsgp_plan_entry) * c->cfg.population_size, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
