@@ -220,7 +220,8 @@ def main():
     sym = host.create_T_F()
     init_trees = host.initialize_population(0)
 
-    def setup(rng_mode):
+    def setup(rng_mode, pipeline="fused"):
+        os.environ["GSGP_PIPELINE"] = pipeline            # read by gsgp_create
         e = Engine(rng_mode=rng_mode, nccl_id=fresh_nccl_id(), **common)
         e.set_dataset(X, y)
         e.set_constants(sym)
@@ -258,18 +259,35 @@ def main():
     e.close()
     value = updates_per_step * K / (ms_dev * 1e-3)
 
+    # ---- the same generations through the unfused pipeline (interp_kernel -> gsop_kernel): the HBM-bound GS
+    # kernel on its own, for the roofline target north_star states for it --------------------------------
+    Ku = max(3, min(K, 10))
+    e, _, _ = setup(capi.RNG_DEVICE_PHILOX, "unfused")
+    e.run_generations(W)
+    e.sync()
+    e.profile_enable(True)
+    barrier()
+    e.run_generations(Ku)
+    e.sync()
+    barrier()
+    prof_u = {k: e.profile_read(k) for k in (capi.K_INTERP, capi.K_GSOP)}
+    e.profile_enable(False)
+    e.close()
+
     # ---- e2e: host-replay mode through gsgp_generation() with host buffers -------------------------
     e, fit, best = setup(capi.RNG_HOST_REPLAY)
     h2d = d2h = 0
-    def replay_step():
+    def replay_step(count=False):
         nonlocal fit, best, h2d, d2h
         plan, pool = host.build_plan(fit, best)
         fit, fit_test, best = e.generation(plan, pool)
-        # uploaded by the call: plan entries, postfix programs (one u16 per node; a tree of i ints
-        # has (i+1)/2 nodes), program offset/length tables
-        h2d = plan.nbytes + int((plan["tree0_len"] + 1)[plan["tree0_len"] > 0].sum()
-                                + (plan["tree1_len"] + 1)[plan["tree1_len"] > 0].sum()) + 16 * P
-        d2h = 16 * P + 4
+        if count:
+            # uploaded by the call: plan entries, accumulator programs (8 B per function node; a tree of i ints
+            # has (i-1)/4 function nodes), program offset/descriptor tables; read back: 2 fitness vectors + best
+            nodes = int(((plan["tree0_len"] - 1) // 4)[plan["tree0_len"] > 0].sum()
+                        + ((plan["tree1_len"] - 1) // 4)[plan["tree1_len"] > 0].sum())
+            h2d = plan.nbytes + 8 * nodes + 16 * P
+            d2h = 16 * P + 4
     for _ in range(W):
         replay_step()
     barrier()
@@ -277,7 +295,9 @@ def main():
     for _ in range(K):
         replay_step()
     barrier()
-    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    t1 = time.perf_counter()
+    replay_step(count=True)
+    ms_e2e = max_over_ranks((t1 - t0) * 1e3)
     e2e_value = updates_per_step * K / (ms_e2e * 1e-3)
     e.close()
     clocks = sampler.stop()
@@ -299,12 +319,28 @@ def main():
         bpu = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
         kname = "gsop_kernel (GS crossover/mutation/reproduction + error reduction)"
     achieved = local_updates * bpu * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this
+    # workload (profiles/README.md); null for workloads that were not captured
+    traffic = {("cfg2", True): 1.756e9, ("cfg2", False): 2.887e9}.get((args.workload, fused)) if world == 1 else None
+    n_gu, ms_gu, _ = prof_u[capi.K_GSOP]
+    n_iu, ms_iu, _ = prof_u[capi.K_INTERP]
+    bpu_u = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
+    ach_u = local_updates * bpu_u * Ku / (ms_gu * 1e-3) / 1e9 if ms_gu > 0 else None
+    gs_unfused = {"kernel": "gsop_kernel (GS crossover/mutation/reproduction + error reduction), unfused pipeline",
+                  "bound": "hbm", "achieved": ach_u, "peak": peak, "unit": "GB/s", "frac": (ach_u / peak) if ach_u else None,
+                  "bytes_per_update": bpu_u, "launches": n_gu, "ms_per_launch": ms_gu / max(1, n_gu),
+                  "interp_kernel_ms_per_launch": ms_iu / max(1, n_iu),
+                  "traffic": {("cfg2"): 2.887e9}.get(args.workload) if world == 1 else None,
+                  "note": "same generations with GSGP_PIPELINE=unfused; not the timed `value` path"}
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": peak_src, "bytes_per_update": bpu,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_update": bpu,
                 "launches": n_gs, "ms_total": ms_gs, "pipeline": "fused" if fused else "unfused",
                 "interp_kernel": {"launches": n_it, "ms_total": ms_it},
-                "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None}}
+                "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None},
+                "limiter": ("instruction issue (ncu: issue-active 69 %, fp64 pipe 40 %, DRAM 23 %): the fused kernel is "
+                            "not HBM-bound; see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
+                "gs_kernel_unfused": gs_unfused}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -31,13 +31,23 @@ struct gsgph_rng {
             if (f != 1.0) return f;
         }
     }
+    // Int31n (Go math/rand v1): rejection above the largest multiple of n, then v % n.  The driver draws with
+    // a handful of distinct n (2, 4, nvar, nconst, population): the threshold and a 64-bit reciprocal for the
+    // modulo are cached per n (exact: q = (v * m) >> 63 is floor(v / n) for v < 2^31, m = ceil(2^63 / n)).
+    struct IntnCache { int32_t n = 0, mx = 0; uint64_t m = 0; } cache[4];
     int32_t intn(int32_t n)
     {
         if ((n & (n - 1)) == 0) return int31() & (n - 1);
-        const int32_t mx = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)n);
+        IntnCache &c = cache[(uint32_t)n & 3u];
+        if (c.n != n) {
+            c.n = n;
+            c.mx = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)n);
+            c.m = (((uint64_t)1 << 63) + (uint64_t)n - 1) / (uint64_t)n;
+        }
         int32_t v = int31();
-        while (v > mx) v = int31();
-        return v % n;
+        while (v > c.mx) v = int31();
+        const uint32_t q = (uint32_t)(((unsigned __int128)(uint64_t)v * c.m) >> 63);
+        return v - (int32_t)(q * (uint32_t)n);
     }
 };
 
