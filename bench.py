@@ -321,7 +321,7 @@ def main():
     achieved = local_updates * bpu * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this
     # workload (profiles/README.md); null for workloads that were not captured
-    traffic = {("cfg2", True): 1.756e9, ("cfg2", False): 2.887e9}.get((args.workload, fused)) if world == 1 else None
+    traffic = {("cfg2", True): 1.756e9, ("cfg2", False): 2.906e9}.get((args.workload, fused)) if world == 1 else None
     n_gu, ms_gu, _ = prof_u[capi.K_GSOP]
     n_iu, ms_iu, _ = prof_u[capi.K_INTERP]
     bpu_u = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
@@ -330,7 +330,7 @@ def main():
                   "bound": "hbm", "achieved": ach_u, "peak": peak, "unit": "GB/s", "frac": (ach_u / peak) if ach_u else None,
                   "bytes_per_update": bpu_u, "launches": n_gu, "ms_per_launch": ms_gu / max(1, n_gu),
                   "interp_kernel_ms_per_launch": ms_iu / max(1, n_iu),
-                  "traffic": {("cfg2"): 2.887e9}.get(args.workload) if world == 1 else None,
+                  "traffic": {("cfg2"): 2.906e9}.get(args.workload) if world == 1 else None,
                   "note": "same generations with GSGP_PIPELINE=unfused; not the timed `value` path"}
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

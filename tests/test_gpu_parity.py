@@ -382,3 +382,99 @@ def test_sigmoid_accuracy_scan():
     assert_close(got[1], want[1], 1e-12, "mutation delta")             # difference of two sigmoids (cancellation)
     assert_close(got[2], want[2], TOL, "crossover")
     e.close(); o.close()
+
+
+def test_full_size_cfg2_properties_and_spot_parity():
+    """BASELINE config 2 at full size (20 vars x 100k cases, pop 1000) through size-independent properties,
+    plus oracle parity on a handful of individuals (the oracle evaluates single rows at 100k cases in ms)."""
+    g = _engine_mod()
+    from go_gsgp_b200.host import HostDriver
+    N, V, P = 100_000, 20, 1000
+    X, y, nrow = synth_dataset(2, N, V)
+    host = HostDriver(population_size=P, nvar=V, seed=1)
+    sym = host.create_T_F()
+    trees = host.initialize_population(0)
+    e = g.Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=ob.RMSE)
+    e.set_dataset(X, y)
+    e.set_constants(sym)
+    e.eval_initial(0, trees)
+    fit, fit_test, best = e.fitness_all()
+    assert best == host.best_individual(fit)
+    # oracle spot check of the initial population
+    cfg = ob.make_config(population_size=P, error_measure=ob.RMSE)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    picks = [0, 1, 17, 500, 999, best]
+    old = {k: e.get_semantic(k) for k in picks}
+    for k in picks:
+        ref = o.semantic_evaluate_array(trees[k])
+        np.testing.assert_array_equal(old[k], ref)                      # tree semantics: bit-exact
+        assert rel_err(fit[k], o.fitness_train(ref[:nrow])) <= TOL
+        assert rel_err(fit_test[k], o.fitness_test(ref[nrow:])) <= TOL
+    # one generation from a hand-made plan that exercises every operator with known outcomes
+    plan = np.zeros(P, ob.PLAN_DTYPE)
+    pool = np.array([1, 3, 4, 4, 4,            # (- x0 x0) == 0  -> sigma = 0.5
+                     0, 3, 4, 5, 6,            # (+ x1 x2)
+                     0, 3, 4, 5, 6], np.int32) # same tree again
+    for k in range(P):
+        m = k % 4
+        if k == best:
+            plan[k] = (ob.OP_XO, 1, k, -1, -1, 0, -1, 0, 0.0)             # elite: carried over
+        elif m == 0:
+            plan[k] = (ob.OP_XO, 0, (k + 1) % P, (k + 7) % P, 0, 5, -1, 0, 0.0)      # R == 0: child = .5 p1 + .5 p2
+        elif m == 1:
+            plan[k] = (ob.OP_MUT, 0, (k + 3) % P, -1, 5, 5, 10, 5, 0.73)            # R1 == R2: child == parent
+        elif m == 2:
+            plan[k] = (ob.OP_REPR, 0, (k + 5) % P, -1, -1, 0, -1, 0, 0.0)           # copy
+        else:
+            plan[k] = (ob.OP_XO, 0, (k + 2) % P, (k + 9) % P, 5, 5, -1, 0, 0.0)     # a real crossover
+    nfit, nfit_test, nbest = e.generation(plan, pool)
+    # the old generation was overwritten by the flip: rebuild the parents from their (known) trees
+    def parent(i):
+        return o.semantic_evaluate_array(trees[i])
+    for k in (best, 4, 8, 5, 9, 6, 10, 7, 11):
+        if k == best:
+            np.testing.assert_array_equal(e.get_semantic(k), parent(k)); assert nfit[k] == fit[k]
+            continue
+        m, row = k % 4, e.get_semantic(k)
+        if m == 0:
+            p1, p2 = parent((k + 1) % P), parent((k + 7) % P)
+            np.testing.assert_array_equal(row, p1 * 0.5 + p2 * 0.5)
+        elif m == 1:
+            np.testing.assert_array_equal(row, parent((k + 3) % P))
+        elif m == 2:
+            np.testing.assert_array_equal(row, parent((k + 5) % P))
+            assert nfit[k] == fit[(k + 5) % P] and nfit_test[k] == fit_test[(k + 5) % P]        # fitness copied, not recomputed
+        else:
+            p1, p2 = parent((k + 2) % P), parent((k + 9) % P)
+            with np.errstate(over="ignore"):
+                s = 1.0 / (1.0 + np.exp(-(X[:, 1] + X[:, 2])))
+            assert np.all(rel_err(row, p1 * s + p2 * (1 - s)) <= TOL)
+        if m != 2:
+            assert rel_err(nfit[k], o.fitness_train(row[:nrow])) <= TOL
+            assert rel_err(nfit_test[k], o.fitness_test(row[nrow:])) <= TOL
+    assert nbest == host.best_individual(nfit)
+    e.close(); o.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nrow_test=0),                       # no test set: test fitness is 0/0 = NaN (SURVEY A.13)
+    dict(population_size=1),                 # the single individual is the elite forever
+    dict(tournament_size=1),
+    dict(nrow=17, nrow_test=3),              # smaller than one vector tile
+])
+def test_edge_shapes_lockstep(kw):
+    nrow, nrow_test = kw.pop("nrow", 300), kw.pop("nrow_test", 77)
+    X, y, _ = synth_dataset(1, nrow + nrow_test, 5, nrow=nrow)
+    args = dict(population_size=24, seed=4)
+    args.update(kw)
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, **args)
+    assert best == o.index_best
+    for _ in range(4):
+        o.generation()
+        fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
+        assert best == o.index_best
+        assert_close(fit, o.fit(), TOL, "fit")
+        assert_close(fit_test, o.fit_test(), TOL, "fit_test")
+    assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
+    e.close(); o.close()
