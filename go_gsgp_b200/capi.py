@@ -17,6 +17,7 @@ MSE, RMSE, MAE, MRE = 0, 1, 2, 3
 OP_INIT, OP_XO, OP_MUT, OP_REPR = 0, 1, 2, 3
 RNG_HOST_REPLAY, RNG_DEVICE_PHILOX = 0, 1
 FLAG_KEEP_TREE_SEMANTICS = 1
+FLAG_LINEAR_SCALING = 2
 K_INTERP, K_GSOP, K_FINALIZE, K_PLAN = 0, 1, 2, 3
 
 

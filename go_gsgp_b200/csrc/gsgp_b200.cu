@@ -101,6 +101,9 @@ struct gsgp_ctx {
     int32_t n_symbols = 0;
     int32_t n_tiles = 0;                                      // 2048-case tiles of gsop_kernel
     int32_t n_tiles_gen = 0;                                  // 256-case tiles of gen_kernel
+    bool linsc = false;                                       // GSGP_FLAG_LINEAR_SCALING
+    double tbar = 0.0;                                        // mean of the (global) train targets
+    double *dsums2 = nullptr, *dsums_all2 = nullptr, *dab = nullptr;   // linear scaling: moment sums, a|b per individual
     bool fused = false;                                       // generation = one gen_kernel launch per chunk
     int32_t gen_levels = 2;
     int32_t chunk_inds = 0;                                   // individuals per interp+gsop launch pair
@@ -253,7 +256,8 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     a.mode = mode; a.L = c->L;
     dim3 grid(c->n_tiles, nk);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
-    switch (c->cfg.error_measure) {
+    switch (c->linsc ? GSGP_SUMO : c->cfg.error_measure) {   // linear scaling: this pass only sums the outputs
+    case GSGP_SUMO: gsop_kernel<GSGP_SUMO><<<grid, kGsThreads, 0, c->stream>>>(a); break;
     case GSGP_MAE: gsop_kernel<GSGP_MAE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
     case GSGP_MRE: gsop_kernel<GSGP_MRE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
     default:       gsop_kernel<GSGP_MSE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
@@ -290,7 +294,8 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
     const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg);
     dim3 grid(n_tiles, groups);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
-    switch (c->cfg.error_measure) {
+    switch (c->linsc ? GSGP_SUMO : c->cfg.error_measure) {
+    case GSGP_SUMO: gen_kernel<GSGP_SUMO><<<grid, kGenThreads, smem, c->stream>>>(a); break;
     case GSGP_MAE: gen_kernel<GSGP_MAE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
     case GSGP_MRE: gen_kernel<GSGP_MRE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
     default:       gen_kernel<GSGP_MSE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
@@ -300,20 +305,67 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
 }
 
 // local partials -> (all-gather across ranks) -> fitness -> best-of-generation
-int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_tiles)
+// tile partials -> per-individual local sums -> every rank's sums (rank order is the summation order)
+int reduce_and_gather(gsgp_ctx *c, int mode, int32_t n_tiles, double *local, double *gathered, const double **all)
 {
     const int P = c->cfg.population_size;
     {
-        ReduceArgs r{c->dplan, c->dpartial, c->dsums, P, n_tiles, mode};
+        ReduceArgs r{c->dplan, c->dpartial, local, P, n_tiles, mode};
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
         reduce_partials_kernel<<<(P * 32 + 255) / 256, 256, 0, c->stream>>>(r);
         CU(c, cudaGetLastError());
     }
-    const double *sums_all = c->dsums;
+    *all = local;
     if (c->cfg.world_size > 1) {
-        ncclResult_t rc = g_nccl.AllGather(c->dsums, c->dsums_all, (size_t)2 * P, ncclDouble, c->comm, c->stream);
+        ncclResult_t rc = g_nccl.AllGather(local, gathered, (size_t)2 * P, ncclDouble, c->comm, c->stream);
         if (rc != ncclSuccess) return fail(c, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
-        sums_all = c->dsums_all;
+        *all = gathered;
+    }
+    return 0;
+}
+
+template <int PASS>
+int launch_ls_pass(gsgp_ctx *c, int mode, const double *sem, const double *osum_all)
+{
+    const int P = c->cfg.population_size;
+    LsArgs a{};
+    a.plan = c->dplan; a.sem = sem; a.y = c->dy; a.partial = c->dpartial; a.osum_all = osum_all; a.ab = c->dab;
+    a.pitch = c->L.n_pad; a.P = P; a.world = c->cfg.world_size; a.n_tiles = c->n_tiles; a.mode = mode;
+    a.nrow = c->cfg.nrow; a.tbar = c->tbar; a.L = c->L;
+    const double n_cases = (double)(c->L.n_tr + c->L.n_te);
+    if (P > 65535) return fail(c, "linear scaling supports populations up to 65535");
+    dim3 grid(c->n_tiles, P);
+    ProfScope ps(c, GSGP_K_GSOP, 8.0 * P * n_cases);
+    if (PASS == LS_MOMENTS) ls_pass_kernel<LS_MOMENTS, GSGP_MSE><<<grid, kGsThreads, 0, c->stream>>>(a);
+    else switch (c->cfg.error_measure) {
+        case GSGP_MAE: ls_pass_kernel<LS_ERROR, GSGP_MAE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
+        case GSGP_MRE: ls_pass_kernel<LS_ERROR, GSGP_MRE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
+        default:       ls_pass_kernel<LS_ERROR, GSGP_MSE><<<grid, kGsThreads, 0, c->stream>>>(a); break;
+    }
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+// local partials -> (all-gather across ranks) -> fitness -> best-of-generation.  n_tiles: tiling of the partials
+// the generation kernels left (gsop: 2048-case tiles, gen_kernel: 256-case tiles)
+int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_tiles)
+{
+    const int P = c->cfg.population_size;
+    const double *sums_all = nullptr;
+    if (reduce_and_gather(c, mode, n_tiles, c->dsums, c->dsums_all, &sums_all)) return 1;
+    if (c->linsc) {
+        // -linsc (main_cpu.go:991-1104,1142-1177): the sums above are the train outputs' sums; centred moments, a and
+        // b, then the error of a + b*o over the new rows
+        const double *osum_all = sums_all, *mom_all = nullptr;
+        if (launch_ls_pass<LS_MOMENTS>(c, mode, c->dsem[new_buf], osum_all)) return 1;
+        if (reduce_and_gather(c, mode, c->n_tiles, c->dsums2, c->dsums_all2, &mom_all)) return 1;
+        {
+            ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+            ls_ab_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(osum_all, mom_all, c->dab, P, c->cfg.world_size, c->cfg.nrow, c->tbar);
+            CU(c, cudaGetLastError());
+        }
+        if (launch_ls_pass<LS_ERROR>(c, mode, c->dsem[new_buf], osum_all)) return 1;
+        if (reduce_and_gather(c, mode, c->n_tiles, c->dsums, c->dsums_all, &sums_all)) return 1;
     }
     {
         FitnessArgs f{c->dplan, sums_all, c->dfit[old_buf], c->dfit_test[old_buf], c->dfit[new_buf],
@@ -561,6 +613,8 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_SUMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        c->linsc = (cfg->flags & GSGP_FLAG_LINEAR_SCALING) != 0;
         // pipeline: fused (one gen_kernel launch per generation, R stays on chip) unless the dataset's columns
         // do not fit shared memory, the caller wants R kept (proto dump), or GSGP_PIPELINE=unfused
         const char *pl = getenv("GSGP_PIPELINE");
@@ -586,6 +640,9 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMalloc((void **)&c->dpartial, sizeof(double) * 2 * (size_t)P * std::max(c->n_tiles, c->n_tiles_gen)));
     CUC(cudaMalloc((void **)&c->dsums, sizeof(double) * 2 * P));
     CUC(cudaMalloc((void **)&c->dsums_all, sizeof(double) * 2 * P * (size_t)cfg->world_size));
+    CUC(cudaMalloc((void **)&c->dsums2, sizeof(double) * 2 * P));
+    CUC(cudaMalloc((void **)&c->dsums_all2, sizeof(double) * 2 * P * (size_t)cfg->world_size));
+    CUC(cudaMalloc((void **)&c->dab, sizeof(double) * 2 * P));
     CUC(cudaMalloc((void **)&c->dplan, sizeof(gsgp_plan_entry) * P));
     CUC(cudaMemsetAsync(c->dplan, 0, sizeof(gsgp_plan_entry) * P, c->stream));
     CUC(cudaMalloc((void **)&c->dprog_off, sizeof(int32_t) * 2 * P));
@@ -658,6 +715,7 @@ void gsgp_destroy(gsgp_ctx *c)
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dsym);
     for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
+    cudaFree(c->dsums2); cudaFree(c->dsums_all2); cudaFree(c->dab);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->ds[i].tree_pool); cudaFree(c->ds[i].prog_desc); cudaFree(c->ds[i].rec); cudaFree(c->ds[i].cand);
@@ -699,6 +757,24 @@ int gsgp_set_dataset_shard(gsgp_ctx *c, const double *train_rows, const double *
         CU(c, cudaGetLastError());
         CU(c, cudaStreamSynchronize(c->stream));
         cudaFree(tmp);
+    }
+    // mean of the train targets for linear scaling (avg_tar main_cpu.go:1078-1083): sequential sum of this rank's
+    // rows; with several ranks the local sums are gathered and added in rank order
+    {
+        double local = 0.0;
+        for (int32_t i = 0; i < c->L.n_tr; ++i) local += train_rows[(size_t)i * (V + 1) + V];
+        double total = local;
+        if (c->cfg.world_size > 1) {
+            CU(c, cudaMemcpyAsync(c->dsums, &local, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            ncclResult_t rc = g_nccl.AllGather(c->dsums, c->dsums_all, 1, ncclDouble, c->comm, c->stream);
+            if (rc != ncclSuccess) return fail(c, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
+            std::vector<double> all((size_t)c->cfg.world_size);
+            CU(c, cudaMemcpyAsync(all.data(), c->dsums_all, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            total = 0.0;
+            for (double v : all) total += v;
+        }
+        c->tbar = c->cfg.nrow > 0 ? total / (double)c->cfg.nrow : 0.0;
     }
     c->have_dataset = true;
     return 0;

@@ -39,7 +39,7 @@ class Engine:
                  tournament_size=4, zero_depth=False, minimization_problem=True, error_measure=capi.MSE,
                  num_constants=0, p_crossover=0.6, p_mutation=0.3, rng_seed=1,
                  rng_mode=capi.RNG_HOST_REPLAY, device=0, rank=0, world_size=1, nccl_id=None,
-                 workspace_bytes=0, flags=0):
+                 workspace_bytes=0, flags=0, use_linear_scaling=False):
         self.L = capi.load()
         cfg = GsgpConfig()
         self.L.gsgp_config_defaults(C.byref(cfg))
@@ -49,6 +49,8 @@ class Engine:
         cfg.error_measure, cfg.num_constants = error_measure, num_constants
         cfg.p_crossover, cfg.p_mutation, cfg.rng_seed = p_crossover, p_mutation, rng_seed
         cfg.rng_mode, cfg.device, cfg.rank, cfg.world_size = rng_mode, device, rank, world_size
+        if use_linear_scaling:                                   # -linsc main_cpu.go:181
+            flags |= capi.FLAG_LINEAR_SCALING
         cfg.workspace_bytes, cfg.flags = workspace_bytes, flags
         if nccl_id is not None:
             C.memmove(cfg.nccl_id, bytes(nccl_id), 128)

@@ -61,7 +61,8 @@ typedef struct {
     int32_t reserved;
 } gsgp_config;
 
-enum { GSGP_FLAG_KEEP_TREE_SEMANTICS = 1  /* keep R of the whole last generation (proto dump) */ };
+enum { GSGP_FLAG_KEEP_TREE_SEMANTICS = 1, /* keep R of the whole last generation (proto dump)                  */
+       GSGP_FLAG_LINEAR_SCALING = 2       /* -linsc: fitness on a + b*semantic (main_cpu.go:181,991-1104,1142-1177) */ };
 
 /* One entry per individual per generation: the decisions of the sequential driver loop
  * (main_cpu.go:1447-1470).  In host-replay mode the host fills it; in device mode the selection

@@ -37,6 +37,8 @@ class OrcConfig(C.Structure):
         ("n_workers", C.c_int32),
         ("rng_kind", C.c_int32),
         ("rng_seed", C.c_int64),
+        ("use_linear_scaling", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -117,6 +119,8 @@ def lib() -> C.CDLL:
         "orc_semantic_evaluate_array": (None, [vp, ip, C.c_int32, C.c_int32, dp]),
         "orc_fitness_train": (C.c_double, [vp, dp]),
         "orc_fitness_test": (C.c_double, [vp, dp]),
+        "orc_fitness_train_ls": (C.c_double, [vp, dp, dp, dp]),
+        "orc_fitness_test_ls": (C.c_double, [vp, dp, C.c_double, C.c_double]),
         "orc_tournament_selection": (C.c_int32, [vp]),
         "orc_best_individual": (C.c_int32, [vp]),
         "orc_better": (C.c_int, [vp, C.c_double, C.c_double]),
@@ -319,6 +323,16 @@ class Oracle:
 
     def fitness_test(self, sem_test: np.ndarray) -> float:
         return self.L.orc_fitness_test(self.h, _dp(np.ascontiguousarray(sem_test, dtype=np.float64)))
+
+    def fitness_train_ls(self, sem_train: np.ndarray):
+        """-> (fitness, a, b)  (fitness_of_semantic_train_ls main_cpu.go:991-1104)"""
+        a, b = C.c_double(), C.c_double()
+        f = self.L.orc_fitness_train_ls(self.h, _dp(np.ascontiguousarray(sem_train, dtype=np.float64)),
+                                        C.cast(C.byref(a), C.POINTER(C.c_double)), C.cast(C.byref(b), C.POINTER(C.c_double)))
+        return f, a.value, b.value
+
+    def fitness_test_ls(self, sem_test: np.ndarray, a: float, b: float) -> float:
+        return self.L.orc_fitness_test_ls(self.h, _dp(np.ascontiguousarray(sem_test, dtype=np.float64)), a, b)
 
     def tournament_selection(self) -> int:
         return self.L.orc_tournament_selection(self.h)

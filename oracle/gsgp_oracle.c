@@ -514,6 +514,116 @@ static double fitness_nls(const orc_state *s, const double *sem, int32_t size, i
 double orc_fitness_train(const orc_state *s, const double *sem) { return fitness_nls(s, sem, s->nrow, 0); }
 double orc_fitness_test(const orc_state *s, const double *sem)  { return fitness_nls(s, sem, s->nrow_test, s->nrow); }
 
+/* ---- linear scaling ------------------------------------------------------------------------ */
+typedef struct { const orc_state *s; const double *sem; int32_t size, offs, block;
+                 double *s_out, *s_tar, *s_oxo, *s_oxt; } ls_sum_job;
+
+static void ls_sum_worker(void *p, int w)                        /* :1009-1024 */
+{
+    ls_sum_job *j = (ls_sum_job *)p;
+    const orc_state *s = j->s;
+    int32_t start = j->block * w, end = j->block * (w + 1);
+    if (end > j->size) end = j->size;
+    size_t stride = (size_t)s->nvar + 1;
+    double so = 0, st = 0, soo = 0, sot = 0;
+    for (int32_t i = j->offs + start; i < j->offs + end; ++i) {
+        double t = s->set[(size_t)i * stride + s->nvar], y = j->sem[i - j->offs];
+        so += y; st += t; soo += y * y; sot += y * t;
+    }
+    j->s_out[w] = so; j->s_tar[w] = st; j->s_oxo[w] = soo; j->s_oxt[w] = sot;
+}
+
+typedef struct { const orc_state *s; const double *sem; int32_t size, offs, block; double a, b; double *par; } ls_err_job;
+
+static void ls_err_worker(void *p, int w)                        /* :1059-1071, :1153-1165 */
+{
+    ls_err_job *j = (ls_err_job *)p;
+    const orc_state *s = j->s;
+    int32_t start = j->block * w, end = j->block * (w + 1);
+    if (end > j->size) end = j->size;
+    size_t stride = (size_t)s->nvar + 1;
+    double acc = 0;
+    for (int32_t i = j->offs + start; i < j->offs + end; ++i)
+        acc += dist(s->cfg.error_measure, s->set[(size_t)i * stride + s->nvar], j->a + j->b * j->sem[i - j->offs]);
+    j->par[w] = acc;
+}
+
+static double ls_error(const orc_state *s, const double *sem, int32_t size, int32_t offs, double a, double b)
+{
+    int W = s->cfg.n_workers;
+    double d = 0;
+    if (W > 1) {
+        double *par = (double *)alloca((size_t)W * 8);
+        memset(par, 0, (size_t)W * 8);
+        ls_err_job j = { s, sem, size, offs, (size + W - 1) / W, a, b, par };
+        pool_run((orc_state *)s, ls_err_worker, &j, W);
+        d = par[0];
+        for (int i = 1; i < W; ++i) d += par[i];
+    } else {
+        size_t stride = (size_t)s->nvar + 1;
+        for (int32_t i = offs; i < offs + size; ++i)
+            d += dist(s->cfg.error_measure, s->set[(size_t)i * stride + s->nvar], a + b * sem[i - offs]);
+    }
+    return post_error(s->cfg.error_measure, d / (double)size);
+}
+
+/* fitness_of_semantic_train_ls :991-1104.  W > 1: four blocked sums, slope from the sum form (:1039-1050);
+ * W == 1: means first, then the centred products (:1076-1095).  b = 0 when den == 0. */
+double orc_fitness_train_ls(const orc_state *s, const double *sem, double *a_out, double *b_out)
+{
+    const int32_t size = s->nrow, offs = 0;
+    int W = s->cfg.n_workers;
+    size_t stride = (size_t)s->nvar + 1;
+    double a, b;
+    if (W > 1) {
+        double *buf = (double *)alloca((size_t)W * 32);
+        memset(buf, 0, (size_t)W * 32);
+        ls_sum_job j = { s, sem, size, offs, (size + W - 1) / W, buf, buf + W, buf + 2 * W, buf + 3 * W };
+        pool_run((orc_state *)s, ls_sum_worker, &j, W);
+        double tot_out = j.s_out[0], tot_tar = j.s_tar[0], tot_oxo = j.s_oxo[0], tot_oxt = j.s_oxt[0];
+        for (int i = 1; i < W; ++i) { tot_out += j.s_out[i]; tot_tar += j.s_tar[i]; tot_oxo += j.s_oxo[i]; tot_oxt += j.s_oxt[i]; }
+        double avg_out = tot_out / (double)size, avg_tar = tot_tar / (double)size;
+        double num = tot_oxt - tot_tar * avg_out - tot_out * avg_tar + (double)size * avg_out * avg_tar;
+        double den = tot_oxo - 2.0 * tot_out * avg_out + (double)size * avg_out * avg_out;
+        b = (den != 0) ? num / den : 0;
+        a = avg_tar - b * avg_out;
+    } else {
+        double avg_out = 0, avg_tar = 0;
+        for (int32_t i = offs; i < size + offs; ++i) { avg_out += sem[i - offs]; avg_tar += s->set[(size_t)i * stride + s->nvar]; }
+        avg_out /= (double)size; avg_tar /= (double)size;
+        double num = 0, den = 0;
+        for (int32_t i = offs; i < offs + size; ++i) {
+            double odiff = sem[i - offs] - avg_out;
+            num += (s->set[(size_t)i * stride + s->nvar] - avg_tar) * odiff;
+            den += odiff * odiff;
+        }
+        b = (den != 0) ? num / den : 0;
+        a = avg_tar - b * avg_out;
+    }
+    if (a_out) *a_out = a;
+    if (b_out) *b_out = b;
+    return ls_error(s, sem, size, offs, a, b);
+}
+
+/* fitness_of_semantic_test_ls :1142-1177: the train a, b applied to the test cases */
+double orc_fitness_test_ls(const orc_state *s, const double *sem, double a, double b)
+{
+    return ls_error(s, sem, s->nrow_test, s->nrow, a, b);
+}
+
+/* fitness_of_semantic_train / _test as main() binds them (:1311-1317) */
+static void fitness_pair(const orc_state *s, const double *sem_train, const double *sem_test, double *fit, double *fit_test)
+{
+    if (s->cfg.use_linear_scaling) {
+        double a, b;
+        *fit = orc_fitness_train_ls(s, sem_train, &a, &b);
+        *fit_test = orc_fitness_test_ls(s, sem_test, a, b);
+    } else {
+        *fit = orc_fitness_train(s, sem_train);
+        *fit_test = orc_fitness_test(s, sem_test);
+    }
+}
+
 /* evaluate :780-795 */
 void orc_evaluate(orc_state *s)
 {
@@ -522,8 +632,7 @@ void orc_evaluate(orc_state *s)
             orc_semantic_evaluate_array(s, s->init_tree[i], s->nrow, 0, s->sem_train[i]);
             orc_semantic_evaluate_array(s, s->init_tree[i], s->nrow_test, s->nrow, s->sem_test[i]);
         }
-        s->fit[i] = orc_fitness_train(s, s->sem_train[i]);
-        s->fit_test[i] = orc_fitness_test(s, s->sem_test[i]);
+        fitness_pair(s, s->sem_train[i], s->sem_test[i], &s->fit[i], &s->fit_test[i]);
     }
     s->index_best = orc_best_individual(s);                      /* :1403 */
 }
@@ -595,9 +704,8 @@ static void xo_apply(orc_state *s, int32_t i, int32_t p1, int32_t p2, const int3
     orc_semantic_evaluate_array(s, rt1, s->nrow, 0, s->rt1_train);
     orc_semantic_evaluate_array(s, rt1, s->nrow_test, s->nrow, s->rt1_test);
     orc_gs_crossover_vec(s->sem_train[p1], s->sem_train[p2], s->rt1_train, s->sem_train_new[i], s->nrow);
-    s->fit_new[i] = orc_fitness_train(s, s->sem_train_new[i]);
     orc_gs_crossover_vec(s->sem_test[p1], s->sem_test[p2], s->rt1_test, s->sem_test_new[i], s->nrow_test);
-    s->fit_test_new[i] = orc_fitness_test(s, s->sem_test_new[i]);
+    fitness_pair(s, s->sem_train_new[i], s->sem_test_new[i], &s->fit_new[i], &s->fit_test_new[i]);   /* :897,:903 */
     keep_rt(s, 0, i, s->rt1_train, s->rt1_test);
 }
 
@@ -609,9 +717,8 @@ static void mut_apply(orc_state *s, int32_t i, double ms, const int32_t *rt1, co
     orc_semantic_evaluate_array(s, rt2, s->nrow, 0, s->rt2_train);
     orc_semantic_evaluate_array(s, rt2, s->nrow_test, s->nrow, s->rt2_test);
     orc_gs_mutation_vec(s->sem_train_new[i], s->rt1_train, s->rt2_train, ms, s->sem_train_new[i], s->nrow);
-    s->fit_new[i] = orc_fitness_train(s, s->sem_train_new[i]);
     orc_gs_mutation_vec(s->sem_test_new[i], s->rt1_test, s->rt2_test, ms, s->sem_test_new[i], s->nrow_test);
-    s->fit_test_new[i] = orc_fitness_test(s, s->sem_test_new[i]);
+    fitness_pair(s, s->sem_train_new[i], s->sem_test_new[i], &s->fit_new[i], &s->fit_test_new[i]);   /* :937,:944 */
     keep_rt(s, 0, i, s->rt1_train, s->rt1_test);
     keep_rt(s, 1, i, s->rt2_train, s->rt2_test);
 }

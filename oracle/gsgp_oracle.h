@@ -76,6 +76,8 @@ typedef struct {                       /* main_cpu.go:70-94, defaults :156-183 *
     int32_t n_workers;                 /* -workers: summation order + fan-out (main_cpu.go:180) */
     int32_t rng_kind;                  /* ORC_RNG_ALFG / ORC_RNG_PHILOX */
     int64_t rng_seed;
+    int32_t use_linear_scaling;        /* -linsc (main_cpu.go:181,1311-1317) */
+    int32_t reserved;
 } orc_config;
 
 void orc_config_defaults(orc_config *c);
@@ -124,6 +126,9 @@ void    orc_semantic_evaluate_array(const orc_state *s, const int32_t *tree,
                                     int32_t sem_size, int32_t sem_offs, double *val); /* :797-827 */
 double  orc_fitness_train(const orc_state *s, const double *sem);          /* :950-985            */
 double  orc_fitness_test(const orc_state *s, const double *sem);           /* :1106-1141          */
+/* linear scaling (-linsc): train returns the fitness and the scaling a, b; test applies the train a, b */
+double  orc_fitness_train_ls(const orc_state *s, const double *sem, double *a, double *b);   /* :991-1104  */
+double  orc_fitness_test_ls(const orc_state *s, const double *sem, double a, double b);      /* :1142-1177 */
 int32_t orc_tournament_selection(orc_state *s);                            /* :830-840            */
 int32_t orc_best_individual(const orc_state *s);                           /* :1180-1188          */
 int     orc_better(const orc_state *s, double f1, double f2);              /* :1206-1212          */

@@ -32,11 +32,13 @@ def main():
         X, y, nrow = synth_dataset(2, 20_003, 7, nrow=15_001)          # ragged: shards of unequal size
         N, V = X.shape
         P = 64
-        cfg = ob.make_config(population_size=P, rng_kind=rng_kind, rng_seed=5, error_measure=ob.RMSE)
+        cfg = ob.make_config(population_size=P, rng_kind=rng_kind, rng_seed=5, error_measure=ob.RMSE,
+                             use_linear_scaling=int(mode == capi.RNG_DEVICE_PHILOX))
         o = ob.Oracle(cfg, X, y, nrow)
         o.create_T_F()
         e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE, rng_seed=5,
-                   rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=fresh_nccl_id())
+                   rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=fresh_nccl_id(),
+                   use_linear_scaling=(mode == capi.RNG_DEVICE_PHILOX))
         e.set_dataset(X, y)
         e.set_constants(o.symbol_values())
         o.initialize_population(0)

@@ -478,3 +478,33 @@ def test_edge_shapes_lockstep(kw):
         assert_close(fit_test, o.fit_test(), TOL, "fit_test")
     assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
     e.close(); o.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(error_measure=ob.RMSE),
+    dict(error_measure=ob.MAE, num_random_constants=3, max_depth_creation=7),
+    dict(error_measure=ob.MSE, rng_kind=ob.RNG_PHILOX),
+    dict(error_measure=ob.MRE, n_workers=3),          # the reference's blocked-sum variant of a, b (:1009-1050)
+])
+def test_linear_scaling_lockstep(kw):
+    """-linsc: fitness on a + b*semantic with a, b fitted on the train cases (main_cpu.go:991-1104,1142-1177)."""
+    X, y, nrow = synth_dataset(1, 3000, 6, nrow=2301)
+    y = 3.0 * y + 10.0                                  # make the scaling matter
+    kw = dict(kw)
+    device = kw.get("rng_kind") == ob.RNG_PHILOX
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=60, seed=8, use_linear_scaling=1, **kw)
+    assert best == o.index_best
+    assert_close(fit, o.fit(), TOL, "initial fit (ls)")
+    assert_close(fit_test, o.fit_test(), TOL, "initial fit_test (ls)")
+    for _ in range(5):
+        o.generation()
+        if device:
+            e.run_generations(1)
+            fit, fit_test, best = e.get_fitness()
+        else:
+            fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
+        assert best == o.index_best
+        assert_close(fit, o.fit(), TOL, "fit (ls)")
+        assert_close(fit_test, o.fit_test(), TOL, "fit_test (ls)")
+    assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
+    e.close(); o.close()

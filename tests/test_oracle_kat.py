@@ -288,3 +288,33 @@ def test_format_float_go_v():
     assert f(5e-324) == "5e-324"
     assert f(float("nan")) == "NaN" and f(float("inf")) == "+Inf" and f(float("-inf")) == "-Inf"
     assert f(123456789.125) == "1.23456789125e+08"
+
+
+@pytest.mark.parametrize("workers", [1, 3])
+def test_linear_scaling_fitness_kat(workers):
+    """-linsc (main_cpu.go:991-1104,1142-1177): b = cov(t, o) / var(o), a = mean(t) - b * mean(o); the error is taken on
+    a + b * o; the test set reuses the train a, b.  Checked against numpy least squares."""
+    rng = np.random.default_rng(5)
+    n, nrow = 400, 300
+    X = rng.normal(size=(n, 3))
+    y = 2.5 * X[:, 0] - 1.0 + 0.1 * rng.normal(size=n)
+    cfg = ob.make_config(population_size=4, error_measure=ob.RMSE, use_linear_scaling=1, n_workers=workers)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    sem = 0.5 * X[:, 0] + 3.0 + 0.05 * rng.normal(size=n)              # a badly scaled but correlated output
+    f, a, b = o.fitness_train_ls(sem[:nrow])
+    bb, aa = np.polyfit(sem[:nrow], y[:nrow], 1)
+    assert abs(a - aa) <= 1e-9 * max(1, abs(aa)) and abs(b - bb) <= 1e-9 * abs(bb)
+    assert abs(f - np.sqrt(np.mean((y[:nrow] - (aa + bb * sem[:nrow])) ** 2))) <= 1e-9 * f
+    ft = o.fitness_test_ls(sem[nrow:], a, b)
+    assert abs(ft - np.sqrt(np.mean((y[nrow:] - (a + b * sem[nrow:])) ** 2))) <= 1e-12 * ft
+    # a constant output has den == 0 -> b = 0, a = mean(t)
+    f0, a0, b0 = o.fitness_train_ls(np.full(nrow, 7.0))
+    assert b0 == 0.0 and abs(a0 - y[:nrow].mean()) <= 1e-12
+    # whole runs use it through evaluate()/crossover/mutation
+    o.initialize_population(0); o.evaluate()
+    for i in range(4):
+        fi, ai, bi = o.fitness_train_ls(o.sem_train(i))
+        assert o.fit()[i] == fi and o.fit_test()[i] == o.fitness_test_ls(o.sem_test(i), ai, bi)
+    o.generation()
+    o.close()
