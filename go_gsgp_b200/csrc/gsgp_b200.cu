@@ -9,6 +9,11 @@
 #include <nccl.h>   // types only: libnccl is dlopen()ed when world_size > 1
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -90,6 +95,83 @@ struct ProfSlot {
     double bytes = 0.0, ms = 0.0;
 };
 
+// Staging workers: compiling ~10^3 random trees per generation is branch-misprediction-bound on one core
+// (random trees = unpredictable control flow), so gsgp_generation spreads the trees over a few persistent
+// threads; each writes its programs into its own buffer, the caller concatenates.
+class StagePool {
+public:
+    struct Job {
+        const int32_t *pool = nullptr, *off = nullptr, *len = nullptr;
+        int32_t pool_len = 0, n_symbols = 0, t0 = 0, t1 = 0;
+        std::vector<Ins> out;                 // programs of slots [t0, t1), concatenated
+        std::vector<int32_t> rel_off, desc;   // per slot: offset inside `out`, prog_desc
+        std::vector<uint8_t> need;
+        std::vector<TreeFrame> frames;
+        int32_t stack_need = 0, bad_slot = -1;
+        const char *err = "";
+        void run()
+        {
+            out.clear(); rel_off.assign((size_t)(t1 - t0), 0); desc.assign((size_t)(t1 - t0), 0);
+            stack_need = 0; bad_slot = -1;
+            size_t total = 1;
+            for (int32_t t = t0; t < t1; ++t) if (len[t] > 0 && off[t] >= 0) total += (size_t)len[t] / 4 + 1;
+            out.resize(total);
+            size_t used = 0;
+            for (int32_t t = t0; t < t1; ++t) {
+                if (len[t] <= 0 || off[t] < 0) continue;
+                if ((int64_t)off[t] + len[t] > pool_len) { bad_slot = t; err = "tree exceeds the tree pool"; return; }
+                int n_ins = 0, nd = 0;
+                if (!compile_prefix_tree(pool + off[t], len[t], n_symbols, out.data() + used, n_ins, nd, need, frames, err)) { bad_slot = t; return; }
+                rel_off[(size_t)(t - t0)] = (int32_t)used; desc[(size_t)(t - t0)] = prog_desc(n_ins, nd);
+                used += (size_t)n_ins;
+                if (nd > stack_need) stack_need = nd;
+            }
+            out.resize(used);
+        }
+    };
+    explicit StagePool(int n_threads) : jobs_((size_t)std::max(1, n_threads))
+    {
+        for (size_t i = 1; i < jobs_.size(); ++i) threads_.emplace_back([this, i] { worker(i); });
+    }
+    ~StagePool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++epoch_; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    std::vector<Job> &jobs() { return jobs_; }
+    void run_all()                                   // job 0 on the caller, the others on the workers
+    {
+        { std::lock_guard<std::mutex> lk(m_); pending_ = (int)jobs_.size() - 1; ++epoch_; }
+        cv_.notify_all();
+        jobs_[0].run();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void worker(size_t i)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+            }
+            jobs_[i].run();
+            { std::lock_guard<std::mutex> lk(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    std::vector<Job> jobs_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    uint64_t epoch_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace
 
 struct gsgp_ctx {
@@ -145,6 +227,12 @@ struct gsgp_ctx {
     PinnedBuf<int32_t> hoff, hlen;
     PinnedBuf<double> hfit;
     PinnedBuf<int32_t> hint;
+    // staging scratch reused across calls (no allocation per tree / per generation on the replay path)
+    std::vector<uint8_t> st_need;
+    std::vector<TreeFrame> st_tframes;
+    std::unique_ptr<StagePool> stage_pool;                    // replay mode, created on first use
+    std::vector<Ins> st_progs;
+    std::vector<int32_t> st_off, st_len;
     std::vector<int32_t> last_pool;                           // replay mode: last generation's trees
     std::vector<gsgp_plan_entry> last_plan;
 
@@ -404,6 +492,29 @@ int launch_best(gsgp_ctx *c, int buf, int32_t gen)
     return 0;
 }
 
+// after the generation kernels: fitness from the partials, update_tables, best_individual
+int finish_generation(gsgp_ctx *c)
+{
+    const int old_buf = c->cur, new_buf = c->cur ^ 1;
+    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, c->fused ? c->n_tiles_gen : c->n_tiles)) return 1;
+    c->cur = new_buf;                                                  // update_tables main_cpu.go:1191-1197
+    c->generation++;
+    if (launch_best(c, c->cur, c->generation)) return 1;               // :1492
+    c->fitness_valid = true;
+    return 0;
+}
+
+// algorithmic bytes of a fused launch over individuals [k0, k0+nk) of a host plan: XO 24 B, MUT 16 B, copy 16 B
+double gen_bytes(const gsgp_plan_entry *plan, int32_t k0, int32_t nk, double n_cases)
+{
+    double b = 0.0;
+    for (int32_t k = k0; k < k0 + nk; ++k) {
+        const bool computed = !plan[k].elite && plan[k].op != GSGP_OP_REPR;
+        b += (computed && plan[k].op == GSGP_OP_XO) ? 24.0 : 16.0;
+    }
+    return b * n_cases;
+}
+
 // the interp -> gsop pipeline of one generation, chunked so that R fits its workspace
 int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may be NULL */, int32_t max_sp)
 {
@@ -433,12 +544,7 @@ int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may 
             if (launch_gsop(c, GS_MODE_GENERATION, k0, nk, k0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
         }
     }
-    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, c->fused ? c->n_tiles_gen : c->n_tiles)) return 1;
-    c->cur = new_buf;                                                  // update_tables main_cpu.go:1191-1197
-    c->generation++;
-    if (launch_best(c, c->cur, c->generation)) return 1;               // :1492
-    c->fitness_valid = true;
-    return 0;
+    return finish_generation(c);
 }
 
 PlanArgs plan_args(gsgp_ctx *c, int32_t generation)
@@ -490,30 +596,23 @@ int launch_select(gsgp_ctx *c, int32_t generation)
 int stage_programs(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len, const int32_t *off,
                    const int32_t *len, std::vector<Ins> &progs, int32_t *hoff, int32_t *hlen, int32_t &stack_need)
 {
-    progs.clear();
     stack_need = 0;
-    std::string err;
-    std::vector<uint16_t> post;
-    std::vector<uint32_t> scratch;
-    std::vector<CompileFrame> frames;
+    const char *err = "";
+    size_t total = 1;
+    for (int32_t t = 0; t < n; ++t) if (len[t] > 0 && off[t] >= 0) total += (size_t)len[t] / 4 + 1;   // function nodes + 1
+    progs.resize(total);
+    size_t used = 0;
     for (int32_t t = 0; t < n; ++t) {
         if (len[t] <= 0 || off[t] < 0) { hoff[t] = 0; hlen[t] = 0; continue; }
         if ((int64_t)off[t] + len[t] > pool_len) return fail(c, "tree %d exceeds the tree pool", t);
-        post.clear();
-        int32_t sp = 0;
-        if (!prefix_to_postfix(pool + off[t], len[t], c->n_symbols, post, sp, err))
-            return fail(c, "tree %d: %s", t, err.c_str());
-        const size_t start = progs.size();
-        progs.resize(start + post.size() / 2 + 1);
-        scratch.resize(post.size());
-        frames.resize(post.size() / 2 + 2);                  // tree depth + 1 <= function nodes + 1
         int n_ins = 0, need = 0;
-        if (!compile_postfix(post.data(), (int)post.size(), progs.data() + start, n_ins, need, scratch.data(), frames.data(), (int)frames.size()))
-            return fail(c, "tree %d: cannot compile", t);
-        progs.resize(start + n_ins);
-        hoff[t] = (int32_t)start; hlen[t] = prog_desc(n_ins, need);
+        if (!compile_prefix_tree(pool + off[t], len[t], c->n_symbols, progs.data() + used, n_ins, need, c->st_need, c->st_tframes, err))
+            return fail(c, "tree %d: %s", t, err);
+        hoff[t] = (int32_t)used; hlen[t] = prog_desc(n_ins, need);
+        used += (size_t)n_ins;
         stack_need = std::max(stack_need, need);
     }
+    progs.resize(used);
     return 0;
 }
 
@@ -900,11 +999,15 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
                     double *fit_out, double *fit_test_out, int32_t *index_best_out)
 {
     if (check_ready(c)) return 1;
+    static const bool trace = getenv("GSGP_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
     if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
     if (!plan) return fail(c, "null plan");
     const int P = c->cfg.population_size;
     CU(c, c->hplan.reserve(P)); CU(c, c->hoff.reserve(2 * (size_t)P)); CU(c, c->hlen.reserve(2 * (size_t)P));
-    std::vector<int32_t> off(2 * (size_t)P), len(2 * (size_t)P);
+    std::vector<int32_t> &off = c->st_off, &len = c->st_len;
+    off.resize(2 * (size_t)P); len.resize(2 * (size_t)P);
     for (int k = 0; k < P; ++k) {
         const gsgp_plan_entry &e = plan[k];
         if (e.op != GSGP_OP_XO && e.op != GSGP_OP_MUT && e.op != GSGP_OP_REPR) return fail(c, "plan[%d]: bad operator %d", k, e.op);
@@ -918,21 +1021,74 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
         off[2 * k + 1] = t1 ? e.tree1_off : -1; len[2 * k + 1] = t1 ? e.tree1_len : 0;
         c->hplan.p[k] = e;
     }
-    std::vector<Ins> progs;
+    auto t1 = now();
+    // compile the generation's trees (compile_prefix_tree) on the staging workers, straight into pinned memory.
+    // GSGP_REPLAY_CHUNKS > 1 cuts the population into chunks so that staging chunk i+1 overlaps gen_kernel of chunk
+    // i; measured slower at config 2 (4 launches: 4 x 0.31 ms vs 0.94 ms, X tiles staged 4 times), so 1 by default.
     int32_t max_sp = 0;
-    if (stage_programs(c, 2 * P, tree_pool, pool_len, off.data(), len.data(), progs, c->hoff.p, c->hlen.p, max_sp)) return 1;
-    CU(c, c->hprog.reserve(progs.size()));
-    memcpy(c->hprog.p, progs.data(), sizeof(Ins) * progs.size());
+    if (!c->stage_pool) {
+        int nt = 4;
+        if (const char *e = getenv("GSGP_STAGE_THREADS")) nt = std::max(1, std::min(16, atoi(e)));
+        nt = std::max(1, std::min<int>(nt, (int)std::thread::hardware_concurrency()));
+        c->stage_pool.reset(new StagePool(nt));
+    }
+    std::vector<StagePool::Job> &jobs = c->stage_pool->jobs();
+    const int32_t nj = (int32_t)jobs.size();
+    size_t prog_cap = 2 * (size_t)P + 1;                               // upper bound: one instruction per function node, >= 1
+    for (int32_t t = 0; t < 2 * P; ++t) if (len[(size_t)t] > 0) prog_cap += (size_t)len[(size_t)t] / 4;
+    CU(c, c->hprog.reserve(prog_cap));
+    CU(c, c->ds[0].prog_pool.reserve(prog_cap));
     c->dcur = 0;
-    CU(c, c->ds[0].prog_pool.reserve(progs.size()));
     CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->ds[0].prog_pool.p, c->hprog.p, sizeof(Ins) * progs.size(), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->dprog_off, c->hoff.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->ds[0].prog_desc, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
-    if (run_generation_kernels(c, c->hplan.p, max_sp)) return 1;
+    static const int32_t env_chunks = getenv("GSGP_REPLAY_CHUNKS") ? atoi(getenv("GSGP_REPLAY_CHUNKS")) : 1;
+    const int32_t n_chunks = (c->fused && P >= 512) ? std::max(1, std::min(env_chunks, 16)) : 1;
+    const double n_cases = (double)(c->L.n_tr + c->L.n_te);
+    size_t base = 0;
+    double us_stage = 0.0;
+    for (int32_t ch = 0; ch < n_chunks; ++ch) {
+        auto ts = now();
+        const int32_t k0 = (int32_t)((int64_t)P * ch / n_chunks), k1 = (int32_t)((int64_t)P * (ch + 1) / n_chunks);
+        const int32_t s0 = 2 * k0, ns = 2 * (k1 - k0);
+        for (int32_t j = 0; j < nj; ++j) {
+            StagePool::Job &J = jobs[(size_t)j];
+            J.pool = tree_pool; J.off = off.data(); J.len = len.data(); J.pool_len = pool_len; J.n_symbols = c->n_symbols;
+            J.t0 = s0 + (int32_t)((int64_t)ns * j / nj); J.t1 = s0 + (int32_t)((int64_t)ns * (j + 1) / nj);
+        }
+        c->stage_pool->run_all();
+        const size_t base0 = base;
+        for (const StagePool::Job &J : jobs) {
+            if (J.bad_slot >= 0) return fail(c, "tree %d: %s", J.bad_slot, J.err);
+            max_sp = std::max(max_sp, J.stack_need);
+            if (!J.out.empty()) memcpy(c->hprog.p + base, J.out.data(), sizeof(Ins) * J.out.size());
+            for (int32_t t = J.t0; t < J.t1; ++t) {
+                const int32_t d = J.desc[(size_t)(t - J.t0)];
+                c->hoff.p[t] = d ? (int32_t)(base + (size_t)J.rel_off[(size_t)(t - J.t0)]) : 0;
+                c->hlen.p[t] = d;
+            }
+            base += J.out.size();
+        }
+        us_stage += std::chrono::duration<double, std::micro>(now() - ts).count();
+        if (base > base0)
+            CU(c, cudaMemcpyAsync(c->ds[0].prog_pool.p + base0, c->hprog.p + base0, sizeof(Ins) * (base - base0), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->dprog_off + s0, c->hoff.p + s0, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->ds[0].prog_desc + s0, c->hlen.p + s0, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, c->stream));
+        if (c->fused &&
+            launch_gen(c, k0, k1 - k0, 0, c->dsem[c->cur], c->dsem[c->cur ^ 1], gen_bytes(c->hplan.p, k0, k1 - k0, n_cases))) return 1;
+    }
+    auto t2 = now(), t3 = t2;
+    if (c->fused) { if (finish_generation(c)) return 1; }
+    else if (run_generation_kernels(c, c->hplan.p, max_sp)) return 1;
+    auto t4 = now();
     c->last_plan.assign(plan, plan + P);
     c->last_pool.assign(tree_pool, tree_pool + std::max(pool_len, 0));
-    return read_fitness(c, fit_out, fit_test_out, index_best_out);
+    auto t5 = now();
+    const int rc = read_fitness(c, fit_out, fit_test_out, index_best_out);
+    if (trace) {
+        auto us = [](auto x, auto y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
+        fprintf(stderr, "gsgp_generation: validate %.0f us, stage+upload+launch chunks %.0f (staging %.0f), finalize launches %.0f, keep plan %.0f, wait+readback %.0f\n",
+                us(t0, t1), us(t1, t2), us_stage, us(t3, t4), us(t4, t5), us(t5, now()));
+    }
+    return rc;
 }
 
 int gsgp_run_generations(gsgp_ctx *c, int32_t n)

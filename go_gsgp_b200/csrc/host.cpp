@@ -204,6 +204,38 @@ int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int
     return overflow ? 1 : 0;
 }
 
+int gsgph_build_effects_plan(gsgph_rng *r, const gsgph_params *p, int32_t test_crossover,
+                             gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t *pool_len)
+{
+    TreeBuilder tb{r, p, {}};
+    int32_t used = 0;
+    bool overflow = false;
+    auto new_tree = [&](int32_t &off, int32_t &len) {
+        const std::vector<int32_t> &t = tb.build(p->max_depth_creation, 0);
+        if (used + (int64_t)t.size() > cap) { overflow = true; off = -1; len = 0; return; }
+        memcpy(pool + used, t.data(), t.size() * sizeof(int32_t));
+        off = used; len = (int32_t)t.size(); used += len;
+    };
+    const int32_t index_best = 0;                                               // operators_effects.go:197 (never assigned)
+    for (int32_t k = 0; k < p->population_size && !overflow; ++k) {
+        gsgp_plan_entry &e = plan[k];
+        e.op = test_crossover ? GSGP_OP_XO : GSGP_OP_MUT; e.elite = (k == index_best); e.p1 = k; e.p2 = -1;
+        e.tree0_off = -1; e.tree0_len = 0; e.tree1_off = -1; e.tree1_len = 0; e.ms = 0.0;
+        if (e.elite) continue;
+        if (test_crossover) {
+            new_tree(e.tree0_off, e.tree0_len);                                 // :803
+            e.p1 = r->intn(p->population_size);                                 // :805 random_selection
+            e.p2 = r->intn(p->population_size);                                 // :806
+        } else {
+            e.ms = r->float64();                                                // :838 (after reproduction(k): self copy)
+            new_tree(e.tree0_off, e.tree0_len);                                 // :840
+            new_tree(e.tree1_off, e.tree1_len);                                 // :841
+        }
+    }
+    if (pool_len) *pool_len = used;
+    return overflow ? 1 : 0;
+}
+
 int32_t gsgph_best_individual(const gsgph_params *p, const double *fit)
 {
     int32_t best = 0;
@@ -216,20 +248,31 @@ int32_t gsgph_best_individual(const gsgph_params *p, const double *fit)
 int gsgph_compile_tree(const int32_t *tree, int32_t len, int32_t n_symbols, uint32_t *code_ab, int32_t cap,
                        int32_t *n_ins, int32_t *spill_levels)
 {
-    std::vector<uint16_t> post;
-    std::string err;
-    int32_t sp = 0;
-    if (!tree || len <= 0 || !gsgp::prefix_to_postfix(tree, len, n_symbols, post, sp, err)) return 1;
-    std::vector<gsgp::Ins> prog(post.size() / 2 + 1);
-    std::vector<uint32_t> scratch(post.size());
-    std::vector<gsgp::CompileFrame> frames(post.size() / 2 + 2);
-    int n = 0, need = 0;
-    if (!gsgp::compile_postfix(post.data(), (int)post.size(), prog.data(), n, need, scratch.data(), frames.data(), (int)frames.size()))
-        return 2;
+    if (!tree || len <= 0) return 1;
+    const char *err = "";
+    std::vector<gsgp::Ins> prog((size_t)len / 4 + 2);
+    std::vector<uint8_t> need;
+    std::vector<gsgp::TreeFrame> frames;
+    int n = 0, nd = 0;
+    if (!gsgp::compile_prefix_tree(tree, len, n_symbols, prog.data(), n, nd, need, frames, err)) return 1;
+    // the device-side builder (plan_draw_kernel) goes through the postfix form: both must agree instruction for instruction
+    {
+        std::vector<uint16_t> post;
+        std::string e2;
+        int32_t sp = 0;
+        if (!gsgp::prefix_to_postfix(tree, len, n_symbols, post, sp, e2)) return 1;
+        std::vector<gsgp::Ins> prog2(post.size() / 2 + 1);
+        std::vector<uint32_t> scratch(post.size());
+        std::vector<gsgp::CompileFrame> fr(post.size() / 2 + 2);
+        int n2 = 0, nd2 = 0;
+        if (!gsgp::compile_postfix(post.data(), (int)post.size(), prog2.data(), n2, nd2, scratch.data(), fr.data(), (int)fr.size())) return 2;
+        if (n2 != n || nd2 != nd) return 4;
+        for (int i = 0; i < n; ++i) if (prog[i].code != prog2[i].code || prog[i].ab != prog2[i].ab) return 4;
+    }
     if (n > cap) return 3;
     for (int i = 0; i < n; ++i) { code_ab[2 * i] = prog[i].code; code_ab[2 * i + 1] = prog[i].ab; }
     if (n_ins) *n_ins = n;
-    if (spill_levels) *spill_levels = need;
+    if (spill_levels) *spill_levels = nd;
     return 0;
 }
 

@@ -31,6 +31,8 @@ HOST_SIGNATURES = {
     "gsgph_build_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.POINTER(C.c_double), C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_best_individual": (C.c_int32, [C.POINTER(HostParams), C.POINTER(C.c_double)]),
+    "gsgph_build_effects_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.c_void_p,
+                                           C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_format_float": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
     "gsgph_compile_tree": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int32,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -122,6 +124,15 @@ class HostDriver:
                                      capi.iptr(self._pool), len(self._pool), C.byref(used))
         if rc:
             raise RuntimeError("gsgph_build_plan: tree pool overflow")
+        return self._plan, self._pool[: max(used.value, 1)]
+
+    def build_effects_plan(self, test_crossover: bool):
+        """operators_effects.go's single step (XO-only with uniform parents, or self-copy + mutation) as a plan."""
+        used = C.c_int32()
+        rc = self.L.gsgph_build_effects_plan(self.rng, C.byref(self.p), int(test_crossover), self._plan.ctypes.data,
+                                             capi.iptr(self._pool), len(self._pool), C.byref(used))
+        if rc:
+            raise RuntimeError("gsgph_build_effects_plan: tree pool overflow")
         return self._plan, self._pool[: max(used.value, 1)]
 
     def best_individual(self, fit) -> int:

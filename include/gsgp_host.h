@@ -50,6 +50,13 @@ int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int
 
 int32_t gsgph_best_individual(const gsgph_params *p, const double *fit);     /* :1180-1188 */
 
+/* the one-step experiment of operators_effects.go:1246-1256 as a plan for gsgp_generation: test_crossover != 0 ->
+ * every individual is a crossover of two UNIFORMLY drawn parents (random_selection :783-786, :800-806); else every
+ * individual is copied onto itself and mutated (:790-797, :836-842).  index_best is never assigned in that program,
+ * so individual 0 plays the elite (:197,:801,:837). */
+int gsgph_build_effects_plan(gsgph_rng *r, const gsgph_params *p, int32_t test_crossover,
+                             gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t *pool_len);
+
 /* The interpreter's program for one tree (csrc/program.hpp), as the shim builds it before upload:
  * pointer-prefix array (main_cpu.go:609-639 format) -> validated postfix -> accumulator program.
  * code_ab receives 2 uint32 per instruction {level<<8 | flags | aop, a | b<<16}; returns non-zero on a

@@ -508,3 +508,27 @@ def test_linear_scaling_lockstep(kw):
         assert_close(fit_test, o.fit_test(), TOL, "fit_test (ls)")
     assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
     e.close(); o.close()
+
+
+@pytest.mark.parametrize("test_crossover", [True, False])
+def test_operators_effects_single_step(test_crossover):
+    """operators_effects.go: one XO-only (uniform parents) or MUT-only (self copy + mutation) step; the plan comes from
+    the host driver, the oracle applies the same plan (generation_replay), the outputs are fit[k] / fit_new[k]."""
+    from go_gsgp_b200.host import HostDriver
+    X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
+    P = 50
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=P, seed=6)
+    host = HostDriver(population_size=P, nvar=5, seed=99)
+    plan, pool = host.build_effects_plan(test_crossover)
+    assert plan["elite"][0] == 1 and not plan["elite"][1:].any()        # individual 0 plays the elite (never-assigned index_best)
+    if test_crossover:
+        assert (plan["op"] == ob.OP_XO).all() and (plan["tree1_len"] == 0).all()
+    else:
+        assert (plan["op"] == ob.OP_MUT).all() and (plan["p1"] == np.arange(P)).all() and (plan["tree1_len"][1:] > 0).all()
+    o.generation_replay(plan.copy(), pool.copy())
+    nfit, nfit_test, _ = e.generation(plan, pool)
+    assert_close(nfit, o.fit(), TOL, "fit_new")
+    assert_close(nfit_test, o.fit_test(), TOL, "fit_test_new")
+    assert nfit[0] == fit[0]
+    assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
+    e.close(); o.close()
