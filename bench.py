@@ -40,6 +40,10 @@ WORKLOADS = {
     # BASELINE.json configs[0]: the CPU-runnable case (latency-bound on a GPU)
     "cfg1": dict(cfg_id=1, nvar=5, cases_per_gpu=1250, pop=100, depth=6, p_xo=0.6, p_mut=0.3,
                  desc="synthetic 5 vars x 1000/250 cases, pop 100"),
+    # BASELINE.json configs[2]: semantic feeding: 500 precomputed semantics (seeded individuals) x 1M cases, pop 2000.
+    # The seeds are generated in memory (y + N(0, 0.05 + 0.001 k)) instead of 500 text files.
+    "cfg3": dict(cfg_id=3, nvar=20, cases_per_gpu=1_000_000, pop=2000, depth=6, p_xo=0.6, p_mut=0.3, n_seeds=500,
+                 desc="semantic feeding: 500 seeded semantics x 1M cases (20 vars), pop 2000, depth 6"),
     # BASELINE.json configs[3]: deep trees, tree-eval bound (pop reduced to fit the default run time)
     "cfg4": dict(cfg_id=4, nvar=20, cases_per_gpu=1_000_000, pop=5000, depth=8, p_xo=0.0, p_mut=1.0,
                  desc="synthetic 20 vars x 1M cases per GPU, pop 5000, depth 8, p_mut 1.0"),
@@ -218,14 +222,19 @@ def main():
     host = HostDriver(population_size=P, nvar=V, max_depth_creation=w["depth"], p_crossover=w["p_xo"],
                       p_mutation=w["p_mut"], seed=1)
     sym = host.create_T_F()
-    init_trees = host.initialize_population(0)
+    n_seeds = w.get("n_seeds", 0)
+    init_trees = host.initialize_population(n_seeds)
+    seed_rng = np.random.Generator(np.random.PCG64(20261019 + 100 * w["cfg_id"]))
+    seeds = [y + seed_rng.normal(0.0, 0.05 + 0.001 * k, size=n_global) for k in range(n_seeds)]   # semantic feeding
 
     def setup(rng_mode, pipeline="fused"):
         os.environ["GSGP_PIPELINE"] = pipeline            # read by gsgp_create
         e = Engine(rng_mode=rng_mode, nccl_id=fresh_nccl_id(), **common)
         e.set_dataset(X, y)
         e.set_constants(sym)
-        e.eval_initial(0, init_trees)
+        for k, sem in enumerate(seeds):                    # main_cpu.go:1383-1388
+            e.seed_semantic(k, sem)
+        e.eval_initial(n_seeds, init_trees)
         fit, fit_test, best = e.fitness_all()
         return e, fit, best
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "gsgp_set_dataset_shard": (C.c_int, [_vp, _dp, _dp]),
     "gsgp_set_constants": (C.c_int, [_vp, _dp, C.c_int32]),
     "gsgp_seed_semantic": (C.c_int, [_vp, C.c_int32, _dp]),
+    "gsgp_seed_semantic_files": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_char_p)]),
     "gsgp_eval_initial": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, C.c_int32, _ip, _ip]),
     "gsgp_fitness_all": (C.c_int, [_vp, _dp, _dp, _ip]),
     "gsgp_generation": (C.c_int, [_vp, _vp, _ip, C.c_int32, _dp, _dp, _ip]),

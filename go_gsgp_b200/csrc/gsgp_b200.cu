@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "../../include/gsgp_host.h"
 #include "trees.hpp"
 
 using namespace gsgp;
@@ -911,6 +912,42 @@ int gsgp_seed_semantic(gsgp_ctx *c, int32_t ind, const double *sem)
     CU(c, cudaStreamSynchronize(c->stream));
     c->fitness_valid = false;
     return 0;
+}
+
+int gsgp_seed_semantic_files(gsgp_ctx *c, int32_t first_ind, int32_t n_files, const char *const *paths)
+{
+    if (check_ready(c)) return 1;
+    if (n_files < 0 || first_ind < 0 || first_ind + (int64_t)n_files > c->cfg.population_size) return fail(c, "individual range out of bounds");
+    if (n_files == 0) return 0;
+    if (!paths) return fail(c, "null path list");
+    const size_t N = (size_t)c->cfg.nrow + (size_t)c->cfg.nrow_test;
+    PinnedBuf<double> buf[2];
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    CU(c, buf[0].reserve(N)); CU(c, buf[1].reserve(N));
+    CU(c, cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    int rc = 0;
+    for (int32_t i = 0; i < n_files && !rc; ++i) {
+        const int b = i & 1;
+        if (i >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = fail(c, "cudaEventSynchronize failed"); break; }
+        const int prc = gsgph_read_semantic(paths[i], (int32_t)N, buf[b].p);      // parses while the previous upload runs
+        if (prc) {
+            rc = fail(c, "%s: %s", paths[i] ? paths[i] : "(null)",
+                      prc == 1 ? "cannot open semantic file" : prc == 2 ? "Cannot parse semantic value" : "Not enough values when reading semantic file");
+            break;
+        }
+        double *row = c->dsem[c->cur] + (size_t)(first_ind + i) * c->L.n_pad;
+        cudaError_t e = cudaSuccess;
+        if (c->L.n_tr) e = cudaMemcpyAsync(row, buf[b].p + c->tr_lo, sizeof(double) * (size_t)c->L.n_tr, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && c->L.n_te)
+            e = cudaMemcpyAsync(row + c->L.tr_pad, buf[b].p + c->cfg.nrow + c->te_lo, sizeof(double) * (size_t)c->L.n_te, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[b], c->stream);
+        if (e != cudaSuccess) rc = fail(c, "semantic upload failed: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    c->fitness_valid = false;
+    return rc;
 }
 
 static int eval_trees_into(gsgp_ctx *c, int32_t n, const int32_t *pool, int32_t pool_len, const int32_t *off,

@@ -4,7 +4,9 @@
 #include "program.hpp"
 #include "trees.hpp"
 
+#include <charconv>
 #include <cmath>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -275,6 +277,136 @@ int gsgph_compile_tree(const int32_t *tree, int32_t len, int32_t n_symbols, uint
     if (spill_levels) *spill_levels = nd;
     return 0;
 }
+
+// ---- ingest ------------------------------------------------------------------------------------------
+namespace {
+
+inline bool is_space(char ch) { return ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\v' || ch == '\f'; }
+
+// tokens of text[b, e): count only (out == nullptr) or parse into out; returns tokens seen, -1 on a bad token
+int64_t scan_tokens(const char *text, int64_t b, int64_t e, double *out)
+{
+    int64_t n = 0, i = b;
+    while (i < e) {
+        while (i < e && is_space(text[i])) ++i;
+        if (i >= e) break;
+        int64_t j = i;
+        while (j < e && !is_space(text[j])) ++j;
+        if (out) {
+            const char *first = text + i, *last = text + j;
+            if (*first == '+' && last - first > 1) ++first;            // strconv.ParseFloat accepts a leading '+'
+            double v = 0.0;
+            const auto r = std::from_chars(first, last, v);
+            if (r.ec == std::errc::result_out_of_range) {              // ParseFloat: +-Inf with ErrRange; atof keeps the value
+                v = std::strtod(std::string(first, last).c_str(), nullptr);
+            } else if (r.ec != std::errc() || r.ptr != last) return -1;
+            out[n] = v;
+        }
+        ++n;
+        i = j;
+    }
+    return n;
+}
+
+bool read_file(const char *path, std::string &buf)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = sz > 0 ? fread(&buf[0], 1, (size_t)sz, f) : 0;
+    fclose(f);
+    return got == buf.size();
+}
+
+}  // namespace
+
+int gsgph_parse_floats(const char *text, int64_t size, double *out, int64_t cap, int64_t *n_out, int32_t n_threads)
+{
+    if (n_threads <= 0) n_threads = (int32_t)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if (size < (1 << 16)) n_threads = 1;
+    // chunk boundaries on whitespace so that no token is split
+    std::vector<int64_t> cut((size_t)n_threads + 1, size);
+    cut[0] = 0;
+    for (int t = 1; t < n_threads; ++t) {
+        int64_t p = size * t / n_threads;
+        while (p < size && !is_space(text[p])) ++p;
+        cut[(size_t)t] = std::max(p, cut[(size_t)t - 1]);
+    }
+    std::vector<int64_t> count((size_t)n_threads, 0);
+    auto run = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto &x : th) x.join();
+    };
+    run([&](int t) { count[(size_t)t] = scan_tokens(text, cut[(size_t)t], cut[(size_t)t + 1], nullptr); });
+    std::vector<int64_t> first((size_t)n_threads + 1, 0);
+    for (int t = 0; t < n_threads; ++t) first[(size_t)t + 1] = first[(size_t)t] + count[(size_t)t];
+    const int64_t total = first[(size_t)n_threads];
+    if (n_out) *n_out = total;
+    // parse: each chunk writes its tokens at its prefix offset; tokens beyond cap are ignored (callers read a prefix)
+    std::vector<int> bad((size_t)n_threads, 0);
+    run([&](int t) {
+        const int64_t f0 = first[(size_t)t];
+        if (f0 >= cap) return;
+        if (f0 + count[(size_t)t] <= cap) { if (scan_tokens(text, cut[(size_t)t], cut[(size_t)t + 1], out + f0) < 0) bad[(size_t)t] = 1; return; }
+        std::vector<double> tmp((size_t)count[(size_t)t]);            // the chunk that straddles cap
+        if (scan_tokens(text, cut[(size_t)t], cut[(size_t)t + 1], tmp.data()) < 0) { bad[(size_t)t] = 1; return; }
+        memcpy(out + f0, tmp.data(), sizeof(double) * (size_t)(cap - f0));
+    });
+    for (int b : bad) if (b) return 2;
+    return 0;
+}
+
+int gsgph_read_semantic(const char *path, int32_t n, double *out)       // read_sem main_cpu.go:710-733
+{
+    std::string buf;
+    if (!path || !read_file(path, buf)) return 1;                       // panic(err)
+    int64_t got = 0;
+    const int rc = gsgph_parse_floats(buf.data(), (int64_t)buf.size(), out, n, &got, 0);
+    if (rc) return 2;                                                   // "Cannot parse semantic value"
+    return got >= n ? 0 : 3;                                            // "Not enough values when reading semantic file"
+}
+
+int gsgph_read_dataset(const char *train_path, const char *test_path, int32_t *nvar, int32_t *nrow, int32_t *nrow_test,
+                       double **rowmajor)                                // read_input_data main_cpu.go:381-421
+{
+    std::string a, b;
+    if (!train_path || !test_path || !read_file(train_path, a) || !read_file(test_path, b)) return 1;
+    auto header = [](const std::string &s, int32_t &v, int32_t &r, int64_t &body) {
+        double h[2]; int64_t n = 0;
+        // the two header tokens: parse a short prefix sequentially
+        int64_t i = 0, seen = 0;
+        while (i < (int64_t)s.size() && seen < 2) {
+            while (i < (int64_t)s.size() && is_space(s[(size_t)i])) ++i;
+            int64_t j = i;
+            while (j < (int64_t)s.size() && !is_space(s[(size_t)j])) ++j;
+            if (j > i) { if (scan_tokens(s.data(), i, j, h + seen) != 1) return false; ++seen; }
+            i = j;
+        }
+        (void)n;
+        if (seen < 2) return false;
+        v = (int32_t)h[0]; r = (int32_t)h[1]; body = i;
+        return v >= 0 && r >= 0 && h[0] == (double)v && h[1] == (double)r;      // atoi: integers
+    };
+    int32_t va = 0, ra = 0, vb = 0, rb = 0; int64_t ba = 0, bb = 0;
+    if (!header(a, va, ra, ba) || !header(b, vb, rb, bb)) return 2;
+    if (va != vb) return 4;                                             // "Train and Test datasets must have the same number of variables"
+    const size_t stride = (size_t)va + 1, na = (size_t)ra * stride, nb = (size_t)rb * stride;
+    double *m = (double *)malloc(sizeof(double) * std::max<size_t>(1, na + nb));
+    if (!m) return 5;
+    int64_t ga = 0, gb = 0;
+    int rc = gsgph_parse_floats(a.data() + ba, (int64_t)a.size() - ba, m, (int64_t)na, &ga, 0);
+    if (!rc) rc = gsgph_parse_floats(b.data() + bb, (int64_t)b.size() - bb, m + na, (int64_t)nb, &gb, 0);
+    if (rc || ga < (int64_t)na || gb < (int64_t)nb) { free(m); return rc ? 2 : 3; }
+    *nvar = va; *nrow = ra; *nrow_test = rb; *rowmajor = m;
+    return 0;
+}
+
+void gsgph_free(void *p) { free(p); }
 
 int gsgph_format_float(double v, char *buf, int32_t cap)
 {

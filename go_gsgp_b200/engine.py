@@ -122,6 +122,11 @@ class Engine:
         assert sem.shape == (self.cfg.nrow + self.cfg.nrow_test,)
         self._ck(self.L.gsgp_seed_semantic(self.h, ind, capi.dptr(sem)))
 
+    def seed_semantic_files(self, first_ind, paths):
+        """semantic feeding from the reference's positional files (main_cpu.go:1342-1349,1383-1388)."""
+        arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+        self._ck(self.L.gsgp_seed_semantic_files(self.h, first_ind, len(paths), arr))
+
     # ------------------------------------------------------------------ evaluate()
     def eval_initial(self, first_ind, trees):
         pool, off, ln = pack_trees(trees)

@@ -34,6 +34,11 @@ HOST_SIGNATURES = {
     "gsgph_build_effects_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.c_void_p,
                                            C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_format_float": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
+    "gsgph_read_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.POINTER(C.c_double))]),
+    "gsgph_read_semantic": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_double)]),
+    "gsgph_free": (None, [C.c_void_p]),
+    "gsgph_parse_floats": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64), C.c_int32]),
     "gsgph_compile_tree": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int32,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
@@ -56,6 +61,30 @@ def format_float(v: float) -> str:
     buf = C.create_string_buffer(64)
     _lib().gsgph_format_float(float(v), buf, 64)
     return buf.value.decode()
+
+
+def read_dataset(train_path, test_path):
+    """read_input_data (main_cpu.go:381-421) -> (X (N,V), y (N,), nrow); raises like the reference panics."""
+    nv, nr, nt = C.c_int32(), C.c_int32(), C.c_int32()
+    ptr = C.POINTER(C.c_double)()
+    rc = _lib().gsgph_read_dataset(str(train_path).encode(), str(test_path).encode(), C.byref(nv), C.byref(nr), C.byref(nt), C.byref(ptr))
+    if rc:
+        raise RuntimeError({1: "cannot open dataset file", 3: "not enough values in dataset file",
+                            4: "Train and Test datasets must have the same number of variables"}.get(rc, "cannot parse dataset file"))
+    n, v = nr.value + nt.value, nv.value
+    m = np.ctypeslib.as_array(ptr, shape=(n, v + 1)).copy()
+    _lib().gsgph_free(ptr)
+    return m[:, :v].copy(), m[:, v].copy(), nr.value
+
+
+def read_semantic(path, n):
+    """read_sem (main_cpu.go:710-733): n values, one per line."""
+    out = np.empty(n)
+    rc = _lib().gsgph_read_semantic(str(path).encode(), n, capi.dptr(out))
+    if rc:
+        raise RuntimeError({1: "cannot open semantic file", 2: "Cannot parse semantic value",
+                            3: "Not enough values when reading semantic file"}[rc])
+    return out
 
 
 def compile_tree(tree, n_symbols):

@@ -99,6 +99,10 @@ int gsgp_set_dataset_shard(gsgp_ctx *ctx, const double *train_rows, const double
 int gsgp_set_constants(gsgp_ctx *ctx, const double *sym_val, int32_t n_symbols);
 /* semantic feeding (main_cpu.go:1383-1388): sem = nrow+nrow_test GLOBAL values, train first */
 int gsgp_seed_semantic(gsgp_ctx *ctx, int32_t ind, const double *sem);
+/* the same from the reference's semantic files (read_sem main_cpu.go:710-733, one value per line): file i seeds
+ * individual first_ind + i.  Parsing (multi-threaded, include/gsgp_host.h) of file i+1 overlaps the upload of file i
+ * through two pinned buffers.  Fails like the reference panics: unreadable file, bad value, too few values. */
+int gsgp_seed_semantic_files(gsgp_ctx *ctx, int32_t first_ind, int32_t n_files, const char *const *paths);
 
 /* ---- evaluate() (main_cpu.go:780-795) ------------------------------------------------------ */
 /* tree -> semantics for individuals [first_ind, first_ind+n): the tree_to_array +

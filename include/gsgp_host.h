@@ -65,6 +65,17 @@ int gsgph_build_effects_plan(gsgph_rng *r, const gsgph_params *p, int32_t test_c
 int gsgph_compile_tree(const int32_t *tree, int32_t len, int32_t n_symbols, uint32_t *code_ab, int32_t cap,
                        int32_t *n_ins, int32_t *spill_levels);
 
+/* ---- ingest: the reference's text formats, parsed fast ---------------------------------------------
+ * Whole-file read, tokens split over worker threads, std::from_chars (correctly rounded, like strconv.ParseFloat).
+ * Same files as read_input_data (main_cpu.go:381-421: `nvar`, `nrow`, then nrow x (nvar+1) whitespace-separated
+ * floats, train file then test file) and read_sem (:710-733: one value per line, nrow+nrow_test of them). */
+int gsgph_read_dataset(const char *train_path, const char *test_path, int32_t *nvar, int32_t *nrow, int32_t *nrow_test,
+                       double **rowmajor /* (nrow+nrow_test) x (nvar+1), malloc'd: release with gsgph_free */);
+int gsgph_read_semantic(const char *path, int32_t n, double *out);   /* non-zero: cannot open / bad value / too few values */
+void gsgph_free(void *p);
+/* the tokenizer/parser behind both: n_threads <= 0 picks a default */
+int gsgph_parse_floats(const char *text, int64_t size, double *out, int64_t cap, int64_t *n_out, int32_t n_threads);
+
 /* Go fmt %v of a float64 (fitness / semantic output lines, main_cpu.go:123-126,1405-1409) */
 int gsgph_format_float(double v, char *buf, int32_t cap);
 

@@ -532,3 +532,32 @@ def test_operators_effects_single_step(test_crossover):
     assert nfit[0] == fit[0]
     assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
     e.close(); o.close()
+
+
+def test_semantic_feeding_from_files(tmp_path):
+    """Positional semantic files (read_sem main_cpu.go:710-733) -> seeded individuals, through the pipelined file path."""
+    g = _engine_mod()
+    X, y, nrow = synth_dataset(3, 5000, 5)
+    N, S, P = len(y), 5, 12
+    rng = np.random.default_rng(12)
+    seeds, paths = [], []
+    for k in range(S):
+        s = y + rng.normal(0, 0.05 + 0.001 * k, size=N)
+        p = tmp_path / f"mod_{k}.dat"
+        p.write_text("".join(repr(float(v)) + "\n" for v in s))
+        seeds.append(s); paths.append(p)
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=P, seeds=seeds)
+    e2 = g.Engine(population_size=P, nvar=5, nrow=nrow, nrow_test=N - nrow, error_measure=ob.RMSE)
+    e2.set_dataset(X, y)
+    e2.set_constants(o.symbol_values())
+    e2.seed_semantic_files(0, paths)
+    e2.eval_initial(S, [o.initial_tree(i) for i in range(S, P)])
+    fit2, fit_test2, best2 = e2.fitness_all()
+    np.testing.assert_array_equal(fit2, fit); np.testing.assert_array_equal(fit_test2, fit_test)
+    assert best2 == best
+    for k in range(S):
+        np.testing.assert_array_equal(e2.get_semantic(k), seeds[k])
+    with pytest.raises(g.GsgpError, match="Not enough values"):
+        short = tmp_path / "short.dat"; short.write_text("1.0\n2.0\n")
+        e2.seed_semantic_files(0, [short])
+    e.close(); e2.close(); o.close()

@@ -1,0 +1,87 @@
+"""Fast ingest of the reference's text formats (include/gsgp_host.h) against the oracle's plain restatements of
+read_input_data (main_cpu.go:381-421) and read_sem (:710-733): bit-identical values, same failure cases."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from go_gsgp_b200 import build
+from go_gsgp_b200.host import read_dataset, read_semantic
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    build.build()
+    ob.build()
+
+
+def write_dataset(path, X, y, sep="\t"):
+    with open(path, "w") as f:                                # README.md:31-42 / runner.py:213 (tabs)
+        f.write(f"{X.shape[1]}\n{X.shape[0]}\n")
+        for r, t in zip(X, y):
+            f.write(sep.join(repr(float(v)) for v in r) + sep + repr(float(t)) + "\n")
+
+
+def oracle_read_dataset(train, test):
+    L = ob.lib()
+    nv, nr, nt = C.c_int32(), C.c_int32(), C.c_int32()
+    ptr = C.POINTER(C.c_double)()
+    L.orc_read_dataset.restype = C.c_int
+    L.orc_read_dataset.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                   C.POINTER(C.POINTER(C.c_double))]
+    rc = L.orc_read_dataset(train.encode(), test.encode(), C.byref(nv), C.byref(nr), C.byref(nt), C.byref(ptr))
+    assert rc == 0
+    n = nr.value + nt.value
+    return np.ctypeslib.as_array(ptr, shape=(n, nv.value + 1)).copy(), nr.value
+
+
+def test_dataset_files_match_the_reference_reader(tmp_path):
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(3000, 7)) * 10.0 ** rng.integers(-8, 8, size=(3000, 7))
+    y = rng.normal(size=3000)
+    X[5, 2], X[6, 3], y[7] = 0.0, -0.0, 1e-310                  # zeros and a subnormal
+    tr, te = str(tmp_path / "train.txt"), str(tmp_path / "test.txt")
+    write_dataset(tr, X[:2400], y[:2400])
+    write_dataset(te, X[2400:], y[2400:], sep="  ")
+    Xr, yr, nrow = read_dataset(tr, te)
+    assert nrow == 2400 and Xr.shape == X.shape
+    np.testing.assert_array_equal(Xr.view(np.uint64), X.view(np.uint64))          # repr round-trips: bit-identical
+    np.testing.assert_array_equal(yr.view(np.uint64), y.view(np.uint64))
+    m, onrow = oracle_read_dataset(tr, te)
+    assert onrow == nrow
+    np.testing.assert_array_equal(np.concatenate([Xr, yr[:, None]], axis=1).view(np.uint64), m.view(np.uint64))
+    # failure cases the reference panics on
+    with pytest.raises(RuntimeError, match="cannot open"):
+        read_dataset(tr, str(tmp_path / "missing.txt"))
+    bad = str(tmp_path / "bad.txt")
+    write_dataset(bad, X[:10, :3], y[:10])
+    with pytest.raises(RuntimeError, match="same number of variables"):
+        read_dataset(tr, bad)
+    open(bad, "w").write("2\n3\n1.0 2.0 3.0\n4.0 5.0\n")
+    with pytest.raises(RuntimeError, match="not enough values"):
+        read_dataset(bad, bad)
+
+
+def test_semantic_files(tmp_path):
+    rng = np.random.default_rng(4)
+    n = 200_000
+    sem = rng.normal(size=n) * 10.0 ** rng.integers(-12, 12, size=n)
+    p = str(tmp_path / "mod_0_1.dat")
+    with open(p, "w") as f:
+        for i, v in enumerate(sem):
+            f.write(("+" if i % 1000 == 1 and v > 0 else "") + (f"{v:.17e}" if i % 3 else repr(float(v))) + "\n")
+    got = read_semantic(p, n)
+    np.testing.assert_array_equal(got.view(np.uint64), sem.view(np.uint64))
+    ref = np.empty(n)
+    L = ob.lib()
+    L.orc_read_sem.restype, L.orc_read_sem.argtypes = C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_double)]
+    assert L.orc_read_sem(p.encode(), n, ref.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
+    np.testing.assert_array_equal(read_semantic(p, 1000), sem[:1000])             # a prefix is fine (:719)
+    with pytest.raises(RuntimeError, match="Not enough values"):
+        read_semantic(p, n + 1)
+    open(p, "a").write("abc\n")
+    with pytest.raises(RuntimeError, match="Cannot parse"):
+        read_semantic(p, n + 1)
