@@ -408,34 +408,80 @@ int gsgph_read_dataset(const char *train_path, const char *test_path, int32_t *n
 
 void gsgph_free(void *p) { free(p); }
 
+namespace {
+// strconv.FormatFloat(v, 'g', -1, 64) as fmt's %v prints it: shortest round-trip digits (std::to_chars), exponent
+// form when exp < -4 || exp >= 6, at least two exponent digits.  Returns the number of chars written (<= 24).
+inline int format_go_v(double v, char *out)
+{
+    if (std::isnan(v)) { memcpy(out, "NaN", 3); return 3; }
+    if (std::isinf(v)) { memcpy(out, v > 0 ? "+Inf" : "-Inf", 4); return 4; }
+    if (v == 0) { if (std::signbit(v)) { memcpy(out, "-0", 2); return 2; } out[0] = '0'; return 1; }
+    char e[40];
+    const auto r = std::to_chars(e, e + sizeof e, v, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
+    const char *q = e, *endp = r.ptr;
+    char *o = out;
+    if (*q == '-') { *o++ = '-'; ++q; }
+    char mant[24]; int nm = 0;
+    for (; q < endp && *q != 'e'; ++q) if (*q != '.') mant[nm++] = *q;
+    int x = 0; bool neg = false;
+    ++q;                                                    // 'e'
+    if (*q == '-') { neg = true; ++q; } else if (*q == '+') ++q;
+    for (; q < endp; ++q) x = x * 10 + (*q - '0');
+    if (neg) x = -x;
+    if (x < -4 || x >= 6) {
+        *o++ = mant[0];
+        if (nm > 1) { *o++ = '.'; memcpy(o, mant + 1, (size_t)nm - 1); o += nm - 1; }
+        *o++ = 'e'; *o++ = x < 0 ? '-' : '+';
+        int ax = x < 0 ? -x : x;
+        if (ax >= 100) { *o++ = (char)('0' + ax / 100); ax %= 100; }
+        *o++ = (char)('0' + ax / 10); *o++ = (char)('0' + ax % 10);
+    } else if (x < 0) {
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -x - 1; ++i) *o++ = '0';
+        memcpy(o, mant, (size_t)nm); o += nm;
+    } else {
+        for (int i = 0; i <= x; ++i) *o++ = i < nm ? mant[i] : '0';
+        if (nm > x + 1) { *o++ = '.'; memcpy(o, mant + x + 1, (size_t)(nm - x - 1)); o += nm - x - 1; }
+    }
+    return (int)(o - out);
+}
+}  // namespace
+
 int gsgph_format_float(double v, char *buf, int32_t cap)
 {
-    if (std::isnan(v)) return snprintf(buf, cap, "NaN");
-    if (std::isinf(v)) return snprintf(buf, cap, v > 0 ? "+Inf" : "-Inf");
-    if (v == 0) return snprintf(buf, cap, std::signbit(v) ? "-0" : "0");
-    char e[40];
-    for (int prec = 0; prec < 17; ++prec) {
-        snprintf(e, sizeof e, "%.*e", prec, v);
-        if (strtod(e, nullptr) == v) break;
-    }
-    std::string mant, out;
-    const char *q = e;
-    if (*q == '-') { out += '-'; ++q; }
-    for (; *q && *q != 'e'; ++q) if (*q != '.') mant += *q;
-    const int x = atoi(q + 1);
-    while (mant.size() > 1 && mant.back() == '0') mant.pop_back();
-    if (x < -4 || x >= 6) {
-        out += mant[0];
-        if (mant.size() > 1) { out += '.'; out.append(mant, 1, std::string::npos); }
-        char ex[16]; snprintf(ex, sizeof ex, "e%c%02d", x < 0 ? '-' : '+', std::abs(x));
-        out += ex;
-    } else if (x < 0) {
-        out += "0."; out.append((size_t)(-x - 1), '0'); out += mant;
-    } else {
-        for (int i = 0; i <= x; ++i) out += i < (int)mant.size() ? mant[i] : '0';
-        if ((int)mant.size() > x + 1) { out += '.'; out.append(mant, (size_t)x + 1, std::string::npos); }
-    }
-    return snprintf(buf, cap, "%s", out.c_str());
+    char tmp[32];
+    const int n = format_go_v(v, tmp);
+    if (cap > 0) { const int m = std::min(n, cap - 1); memcpy(buf, tmp, (size_t)m); buf[m] = 0; }
+    return n;
+}
+
+// Semantic.String() (main_cpu.go:123-126): the values in %v form joined by commas; what the best-of-generation
+// semantic lines are made of (:1499-1500).  Multi-threaded; returns non-zero if cap is too small (25 bytes per value
+// always suffice).
+int gsgph_format_semantic(const double *v, int64_t n, char *out, int64_t cap, int64_t *len_out, int32_t n_threads)
+{
+    if (n_threads <= 0) n_threads = (int32_t)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if (n < (1 << 14)) n_threads = 1;
+    std::vector<std::string> part((size_t)n_threads);
+    auto work = [&](int t) {
+        const int64_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
+        std::string &s = part[(size_t)t];
+        s.resize((size_t)(b - a) * 25);
+        char *o = &s[0];
+        for (int64_t i = a; i < b; ++i) { if (i) *o++ = ','; o += format_go_v(v[i], o); }
+        s.resize((size_t)(o - s.data()));
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    int64_t total = 0;
+    for (auto &s : part) total += (int64_t)s.size();
+    if (len_out) *len_out = total;
+    if (total > cap) return 1;
+    int64_t at = 0;
+    for (auto &s : part) { memcpy(out + at, s.data(), s.size()); at += (int64_t)s.size(); }
+    return 0;
 }
 
 }  // extern "C"

@@ -34,6 +34,7 @@ HOST_SIGNATURES = {
     "gsgph_build_effects_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.c_void_p,
                                            C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_format_float": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
+    "gsgph_format_semantic": (C.c_int, [C.POINTER(C.c_double), C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.c_int32]),
     "gsgph_read_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.POINTER(C.c_double))]),
     "gsgph_read_semantic": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_double)]),
@@ -61,6 +62,17 @@ def format_float(v: float) -> str:
     buf = C.create_string_buffer(64)
     _lib().gsgph_format_float(float(v), buf, 64)
     return buf.value.decode()
+
+
+def format_semantic(sem) -> str:
+    """Semantic.String() (main_cpu.go:123-126): "3.14,2.71,1.41"."""
+    sem = np.ascontiguousarray(sem, np.float64)
+    cap = 25 * max(1, len(sem))
+    buf = C.create_string_buffer(cap)
+    n = C.c_int64()
+    rc = _lib().gsgph_format_semantic(capi.dptr(sem), len(sem), buf, cap, C.byref(n), 0)
+    assert rc == 0
+    return buf.raw[: n.value].decode()
 
 
 def read_dataset(train_path, test_path):

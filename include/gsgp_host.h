@@ -78,6 +78,9 @@ int gsgph_parse_floats(const char *text, int64_t size, double *out, int64_t cap,
 
 /* Go fmt %v of a float64 (fitness / semantic output lines, main_cpu.go:123-126,1405-1409) */
 int gsgph_format_float(double v, char *buf, int32_t cap);
+/* Semantic.String() (main_cpu.go:123-126): %v values joined by commas -- the best-of-generation semantic line
+ * (:1499-1500).  Multi-threaded (n_threads <= 0: default); 25 bytes per value always suffice; non-zero if cap is short. */
+int gsgph_format_semantic(const double *v, int64_t n, char *out, int64_t cap, int64_t *len_out, int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -60,3 +60,20 @@ def test_format_float_matches_go_v():
         if np.isfinite(v):
             assert float(f(v)) == v
     assert f(1e6) == "1e+06" and f(123456.0) == "123456" and f(0.5) == "0.5"
+
+
+def test_format_semantic_line():
+    """Semantic.String() (main_cpu.go:123-126): %v values joined by commas; bulk path == per-value path == oracle."""
+    from go_gsgp_b200.host import format_semantic, format_float
+    rng = np.random.default_rng(1)
+    sem = np.concatenate([rng.normal(size=40_000) * 10.0 ** rng.integers(-20, 20, size=40_000),
+                          [0.0, -0.0, 1e6, 999999.0, 1e-5, 0.0001, 5e-324, 1e100, np.inf, -np.inf, np.nan]])
+    line = format_semantic(sem)
+    parts = line.split(",")
+    assert len(parts) == len(sem)
+    idx = list(range(0, len(sem), 997)) + list(range(len(sem) - 11, len(sem)))
+    for i in idx:
+        assert parts[i] == format_float(sem[i]) == ob.format_float(sem[i])
+    back = np.array([float(p.replace("+Inf", "inf").replace("-Inf", "-inf")) for p in parts])
+    assert np.array_equal(back[:-1], sem[:-1]) and np.isnan(back[-1])        # shortest digits round-trip exactly
+    assert format_semantic(np.array([3.14, 2.71, 1.41])) == "3.14,2.71,1.41"  # the example in the reference's comment
