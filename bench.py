@@ -148,7 +148,8 @@ def run_reference(args):
         "impl": "reference", "metric": "individual-case semantic updates/sec", "value": value, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}"},
+        "config": {"workload": f"{args.workload}: {w['desc']}", "global_cases": n_cases * max(1, args.gpus), "pop": w["pop"],
+                   "l2": "n/a (CPU arm)", "parallelism": "host threads"},
         "cpu_baseline": {"value": value, "unit": "updates/s", "cores": workers, "kind": "port", "sample": sample,
                          "note": "C restatement of main_cpu.go (oracle); go-gsgp itself cannot be built (no Go toolchain)"},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
