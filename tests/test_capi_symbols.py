@@ -72,3 +72,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(txt), f"{f} references the oracle"
+
+
+def test_host_header_symbols_are_exported_and_bound(lib):
+    """include/gsgp_host.h: every declared gsgph_* entry point is exported by the same library and bound."""
+    from go_gsgp_b200 import host
+    src = open(os.path.join(ROOT, "include", "gsgp_host.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(gsgph_[a-z0-9_A-Z]+)\s*\(", src)))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gsgp_host.h but not exported"
+    assert set(names) == set(host.HOST_SIGNATURES), set(names) ^ set(host.HOST_SIGNATURES)

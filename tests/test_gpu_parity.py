@@ -561,3 +561,28 @@ def test_semantic_feeding_from_files(tmp_path):
         short = tmp_path / "short.dat"; short.write_text("1.0\n2.0\n")
         e2.seed_semantic_files(0, [short])
     e.close(); e2.close(); o.close()
+
+
+def test_runs_are_bit_reproducible():
+    """Warps claim work dynamically, but every partial sum has a fixed shape: two runs of the same configuration give
+    bit-identical fitness histories, in the fused and in the unfused pipeline (which also agree with each other to 1e-12)."""
+    g = _engine_mod()
+    X, y, nrow = synth_dataset(2, 30_011, 8)
+    hist = {}
+    for pipeline in ("fused", "fused", "unfused"):
+        os.environ["GSGP_PIPELINE"] = pipeline
+        try:
+            o, e, _ = _mk(X, y, nrow, population_size=200, seed=21, rng_kind=ob.RNG_PHILOX)
+        finally:
+            os.environ.pop("GSGP_PIPELINE", None)
+        e.run_generations(12)
+        bf, bt, bi = e.get_history(0, 13)
+        fit, fit_test, _ = e.get_fitness()
+        hist.setdefault(pipeline, []).append((bf.copy(), bt.copy(), bi.copy(), fit.copy(), fit_test.copy()))
+        e.close(); o.close()
+    a, b = hist["fused"]
+    for x, z in zip(a, b):
+        np.testing.assert_array_equal(x, z)
+    u = hist["unfused"][0]
+    assert np.array_equal(a[2], u[2])                                   # same best individuals
+    assert_close(a[3], u[3], 1e-12, "fused vs unfused fitness")
