@@ -573,7 +573,13 @@ int launch_draw(gsgp_ctx *c, int32_t generation)
     CU(c, cudaStreamWaitEvent(c->stream2, c->ev_free, 0));
     {
         ProfScope ps(c, GSGP_K_PLAN, 0.0, c->stream2);
-        plan_draw_kernel<<<(a.P + 127) / 128, 128, 0, c->stream2>>>(a);
+        // working set of a thread: postfix + builder scratch, post_stride words each, in shared memory when a block of
+        // >= 32 threads fits (depth <= 8); global scratch pools otherwise
+        const size_t per_thread = 2 * (size_t)c->post_stride * sizeof(uint32_t);
+        int nt = 0;
+        for (int cand : {64, 32}) if (per_thread * cand <= (size_t)200 * 1024) { nt = cand; break; }
+        if (nt) plan_draw_kernel<true><<<(a.P + nt - 1) / nt, nt, per_thread * nt, c->stream2>>>(a);
+        else plan_draw_kernel<false><<<(a.P + 127) / 128, 128, 0, c->stream2>>>(a);
         CU(c, cudaGetLastError());
     }
     CU(c, cudaEventRecord(c->ev_draw[generation & 1], c->stream2));
@@ -714,6 +720,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_SUMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(plan_draw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         c->linsc = (cfg->flags & GSGP_FLAG_LINEAR_SCALING) != 0;
         // pipeline: fused (one gen_kernel launch per generation, R stays on chip) unless the dataset's columns
         // do not fit shared memory, the caller wants R kept (proto dump), or GSGP_PIPELINE=unfused

@@ -50,8 +50,11 @@ constexpr int kMaxStackLevels = 32;                    // spill levels the inter
 // Returns false on a malformed program or when frame_cap is too small.
 struct CompileFrame { uint16_t node; uint8_t state, live, first_is_left; };
 
-GSGP_HD bool compile_postfix(const uint16_t *post, int len, Ins *out, int &n_out, int &stack_need,
-                             uint32_t *scratch, CompileFrame *frames, int frame_cap)
+// PostA / ScratchA: anything indexable with [] (plain pointers on the host; bank-interleaved shared-memory views in
+// plan_draw_kernel, where a thread-serial walk over global memory would be latency-bound).
+template <typename PostA, typename ScratchA>
+GSGP_HD bool compile_postfix(PostA post, int len, Ins *out, int &n_out, int &stack_need,
+                             ScratchA scratch, CompileFrame *frames, int frame_cap)
 {
     n_out = 0; stack_need = 0;
     if (len <= 0) return false;
