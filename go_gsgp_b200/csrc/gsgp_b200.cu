@@ -175,6 +175,8 @@ private:
 
 }  // namespace
 
+constexpr int kDrawSets = 3;
+
 struct gsgp_ctx {
     gsgp_config cfg{};
     std::string err;
@@ -201,19 +203,20 @@ struct gsgp_ctx {
     double *dR = nullptr;
     double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
     gsgp_plan_entry *dplan = nullptr;
-    // random trees + programs of a generation.  Host replay uses set 0; device mode alternates between two
-    // sets so that plan_draw_kernel for generation g+1 (second stream) overlaps generation g's arithmetic.
+    // random trees + programs of a generation.  Host replay uses set 0; device mode rotates through three sets:
+    // generation g is consumed from set g%3 while plan_draw_kernel fills the sets of g+1 and g+2 on the second
+    // stream (and the set of g stays readable for gsgp_get_tree until the draws of g+3).
     struct DrawSet {
         int32_t *tree_pool = nullptr;                         // device mode: reference arrays (gsgp_get_tree)
         DevBuf<Ins> prog_pool;                                // accumulator programs (program.hpp)
         int32_t *prog_desc = nullptr;                         // [2P] prog_desc(n, need)
         DrawRec *rec = nullptr;                               // device mode: what plan_draw_kernel drew
         int32_t *cand = nullptr;                              // device mode: tournament candidates
-    } ds[2];
+    } ds[kDrawSets];
     int dcur = 0;                                             // set of the current / last generation
-    int32_t drawn_gen = -1;                                   // generation whose draws sit in ds[drawn_gen & 1]
+    int32_t drawn[kDrawSets] = {-1, -1, -1};                  // generation whose draws sit in (or are on their way to) ds[i]
     cudaStream_t stream2 = nullptr;                           // plan_draw_kernel
-    cudaEvent_t ev_draw[2] = {nullptr, nullptr}, ev_free = nullptr;
+    cudaEvent_t ev_draw[kDrawSets] = {}, ev_free[kDrawSets] = {};   // per draw set: filled / no longer read
     uint16_t *dpost_pool = nullptr;                           // device mode: postfix scratch of plan_draw_kernel
     uint32_t *dcompile_scratch = nullptr;                     // device mode: program-builder scratch
     int32_t *dprog_off = nullptr;
@@ -239,7 +242,7 @@ struct gsgp_ctx {
 
     ncclComm_t comm = nullptr;
     ProfSlot prof[GSGP_K_COUNT];
-    bool profiling = false;
+    int profiling = 0;                                        // 0 off, 1 generation kernels only, 2 every kernel
     int64_t launch_count = 0;
 };
 
@@ -269,7 +272,8 @@ struct ProfScope {                 // CUDA-event bracket around one kernel launc
         c->launch_count++;
         ProfSlot &s = c->prof[k];
         s.launches++;
-        if (!c->profiling) return;
+        // timing events cost ~2 us of stream time each: level 1 brackets only the kernels that matter for the roofline
+        if (!c->profiling || (c->profiling == 1 && k != GSGP_K_GSOP && k != GSGP_K_INTERP)) return;
         if (s.used == s.ev.size()) {
             if (s.ev.size() >= 16384) return;
             cudaEvent_t a, b;
@@ -545,12 +549,14 @@ int run_generation_kernels(gsgp_ctx *c, const gsgp_plan_entry *host_plan /* may 
             if (launch_gsop(c, GS_MODE_GENERATION, k0, nk, k0, c->dsem[old_buf], c->dsem[new_buf], bytes)) return 1;
         }
     }
+    // device mode: the draw set of this generation is no longer read once the kernels above are done
+    if (!host_plan && c->stream2) CU(c, cudaEventRecord(c->ev_free[c->dcur], c->stream));
     return finish_generation(c);
 }
 
 PlanArgs plan_args(gsgp_ctx *c, int32_t generation)
 {
-    gsgp_ctx::DrawSet &d = c->ds[generation & 1];
+    gsgp_ctx::DrawSet &d = c->ds[generation % kDrawSets];
     PlanArgs a{};
     a.plan = c->dplan; a.rec = d.rec; a.cand = d.cand; a.tree_pool = d.tree_pool; a.post_pool = c->dpost_pool;
     a.compile_scratch = c->dcompile_scratch; a.prog_pool = d.prog_pool.p; a.prog_desc = d.prog_desc;
@@ -566,11 +572,11 @@ PlanArgs plan_args(gsgp_ctx *c, int32_t generation)
 }
 
 // everything of generation `generation` that consumes random numbers, on the second stream; it may only
-// overwrite its draw set once the generation that last used it (generation - 2) is done: ev_free
+// overwrite its draw set once the generation that last read it (generation - 2) is done: ev_free[set]
 int launch_draw(gsgp_ctx *c, int32_t generation)
 {
     const PlanArgs a = plan_args(c, generation);
-    CU(c, cudaStreamWaitEvent(c->stream2, c->ev_free, 0));
+    CU(c, cudaStreamWaitEvent(c->stream2, c->ev_free[generation % kDrawSets], 0));
     {
         ProfScope ps(c, GSGP_K_PLAN, 0.0, c->stream2);
         // working set of a thread: postfix + builder scratch, post_stride words each, in shared memory when a block of
@@ -582,8 +588,8 @@ int launch_draw(gsgp_ctx *c, int32_t generation)
         else plan_draw_kernel<false><<<(a.P + 127) / 128, 128, 0, c->stream2>>>(a);
         CU(c, cudaGetLastError());
     }
-    CU(c, cudaEventRecord(c->ev_draw[generation & 1], c->stream2));
-    c->drawn_gen = generation;
+    CU(c, cudaEventRecord(c->ev_draw[generation % kDrawSets], c->stream2));
+    c->drawn[generation % kDrawSets] = generation;
     return 0;
 }
 
@@ -591,8 +597,8 @@ int launch_draw(gsgp_ctx *c, int32_t generation)
 int launch_select(gsgp_ctx *c, int32_t generation)
 {
     const PlanArgs a = plan_args(c, generation);
-    CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[generation & 1], 0));
-    c->dcur = generation & 1;
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[generation % kDrawSets], 0));
+    c->dcur = generation % kDrawSets;
     ProfScope ps(c, GSGP_K_PLAN, 0.0);
     plan_select_kernel<<<(a.P + 255) / 256, 256, 0, c->stream>>>(a);
     CU(c, cudaGetLastError());
@@ -753,7 +759,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMalloc((void **)&c->dplan, sizeof(gsgp_plan_entry) * P));
     CUC(cudaMemsetAsync(c->dplan, 0, sizeof(gsgp_plan_entry) * P, c->stream));
     CUC(cudaMalloc((void **)&c->dprog_off, sizeof(int32_t) * 2 * P));
-    const int n_sets = cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX ? 2 : 1;
+    const int n_sets = cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX ? kDrawSets : 1;
     for (int i = 0; i < n_sets; ++i) {
         CUC(cudaMalloc((void **)&c->ds[i].prog_desc, sizeof(int32_t) * 2 * P));
         CUC(cudaMemsetAsync(c->ds[i].prog_desc, 0, sizeof(int32_t) * 2 * P, c->stream));
@@ -766,7 +772,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         c->post_stride = (1 << (d + 1));                       // nodes <= 2^(d+1)-1
         c->prog_stride = (1 << d);                             // function nodes <= 2^d-1
         c->tree_stride = 4 * (1 << d);                         // ints  <= 4*2^d-3 (main_cpu.go:609-639)
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kDrawSets; ++i) {
             CUC(cudaMalloc((void **)&c->ds[i].tree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
             CUC(c->ds[i].prog_pool.reserve((size_t)2 * P * c->prog_stride));
             CUC(cudaMalloc((void **)&c->ds[i].rec, sizeof(DrawRec) * (size_t)P));
@@ -774,10 +780,16 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         }
         CUC(cudaMalloc((void **)&c->dpost_pool, sizeof(uint16_t) * 2 * (size_t)P * c->post_stride));
         CUC(cudaMalloc((void **)&c->dcompile_scratch, sizeof(uint32_t) * 2 * (size_t)P * c->post_stride));
-        CUC(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_draw[i], cudaEventDisableTiming));
-        CUC(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
-        CUC(cudaEventRecord(c->ev_free, c->stream));
+        {   // the draw kernel is small and on the critical path of the NEXT generation: let its blocks go first
+            int lo = 0, hi = 0;
+            CUC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUC(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+        }
+        for (int i = 0; i < kDrawSets; ++i) {
+            CUC(cudaEventCreateWithFlags(&c->ev_draw[i], cudaEventDisableTiming));
+            CUC(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+            CUC(cudaEventRecord(c->ev_free[i], c->stream));
+        }
         std::vector<int32_t> off(2 * (size_t)P);
         for (int t = 0; t < 2 * P; ++t) off[t] = t * c->prog_stride;
         CUC(cudaMemcpyAsync(c->dprog_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, c->stream));
@@ -824,11 +836,11 @@ void gsgp_destroy(gsgp_ctx *c)
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
     cudaFree(c->dsums2); cudaFree(c->dsums_all2); cudaFree(c->dab);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kDrawSets; ++i) {
         cudaFree(c->ds[i].tree_pool); cudaFree(c->ds[i].prog_desc); cudaFree(c->ds[i].rec); cudaFree(c->ds[i].cand);
         if (c->ev_draw[i]) cudaEventDestroy(c->ev_draw[i]);
     }
-    if (c->ev_free) cudaEventDestroy(c->ev_free);
+    for (int i = 0; i < kDrawSets; ++i) if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaFree(c->dplan); cudaFree(c->dprog_off);
     cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
@@ -1144,13 +1156,14 @@ int gsgp_run_generations(gsgp_ctx *c, int32_t n)
     if (ensure_hist(c, c->generation + n)) return 1;
     for (int32_t i = 0; i < n; ++i) {
         const int32_t g = c->generation + 1;
-        if (c->drawn_gen != g && launch_draw(c, g)) return 1;         // (first call / after gsgp_draw_plan)
+        // draws run two generations ahead on the second stream: those of g+2 start the moment gen_kernel(g) has
+        // released the draw set they overwrite, i.e. under the finalize kernels of g and the start of g+1, when
+        // SMs are free (a gen_kernel block fills an SM's shared memory; a draw block cannot squeeze in beside it)
+        if (c->drawn[g % kDrawSets] != g && launch_draw(c, g)) return 1;       // first calls / after gsgp_draw_plan
+        if (c->drawn[(g + 1) % kDrawSets] != g + 1 && launch_draw(c, g + 1)) return 1;
         if (launch_select(c, g)) return 1;
-        // generation g-1 and the selection of g are queued: set (g+1)&1 is free once they are done; the draws
-        // of g+1 then run on the second stream under generation g's arithmetic
-        CU(c, cudaEventRecord(c->ev_free, c->stream));
-        if (launch_draw(c, g + 1)) return 1;
-        if (run_generation_kernels(c, nullptr, max_sp)) return 1;
+        if (run_generation_kernels(c, nullptr, max_sp)) return 1;              // records ev_free[g%3] behind the kernels that read the set
+        if (launch_draw(c, g + 2)) return 1;                                   // (its set was released by generation g-1)
     }
     c->last_plan.clear();
     return 0;
@@ -1257,10 +1270,11 @@ int gsgp_draw_plan(gsgp_ctx *c, int32_t generation, gsgp_plan_entry *plan_out)
 {
     if (check_ready(c)) return 1;
     if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_draw_plan needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
-    CU(c, cudaEventRecord(c->ev_free, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream2));                          // pre-drawn generations are discarded
+    CU(c, cudaEventRecord(c->ev_free[generation % kDrawSets], c->stream));
     if (launch_draw(c, generation)) return 1;
     if (launch_select(c, generation)) return 1;
-    c->drawn_gen = -1;                                                 // a later run re-draws its own generation
+    for (int i = 0; i < kDrawSets; ++i) c->drawn[i] = -1;              // a later run re-draws its own generations
     c->last_plan.clear();
     CU(c, cudaMemcpyAsync(plan_out, c->dplan, sizeof(gsgp_plan_entry) * c->cfg.population_size, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1272,8 +1286,18 @@ void *gsgp_stream(gsgp_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int gsgp_profile_enable(gsgp_ctx *c, int32_t on)
 {
     if (!c) return 1;
-    c->profiling = on != 0;
+    c->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
     if (on) for (auto &s : c->prof) { s.used = 0; s.launches = 0; s.bytes = 0.0; s.ms = 0.0; }
+    if (on) {                                                  // events are created up front, not inside the timed region
+        for (int k : {GSGP_K_GSOP, GSGP_K_INTERP}) {
+            ProfSlot &s = c->prof[k];
+            while (s.ev.size() < 1024) {
+                cudaEvent_t a, b;
+                if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) break;
+                s.ev.push_back({a, b});
+            }
+        }
+    }
     return 0;
 }
 

@@ -156,6 +156,8 @@ int gsgp_draw_plan(gsgp_ctx *ctx, int32_t generation, gsgp_plan_entry *plan_out)
 void *gsgp_stream(gsgp_ctx *ctx);                        /* cudaStream_t all kernels are issued on */
 /* CUDA-event timing of each kernel family on that stream: enable, run, then read. */
 enum { GSGP_K_INTERP = 0, GSGP_K_GSOP = 1, GSGP_K_FINALIZE = 2, GSGP_K_PLAN = 3, GSGP_K_COUNT = 4 };
+/* on: 0 off; 1 the generation kernels (GSGP_K_INTERP, GSGP_K_GSOP) only -- two timing events per launch cost
+ * ~2 us of stream time each, so the small kernels are left alone; 2 every kernel */
 int gsgp_profile_enable(gsgp_ctx *ctx, int32_t on);
 int gsgp_profile_read(gsgp_ctx *ctx, int32_t kernel, int64_t *launches, double *total_ms,
                       double *algorithmic_bytes);
