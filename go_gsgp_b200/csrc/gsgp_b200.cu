@@ -372,7 +372,8 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
 {
     if (nk <= 0) return 0;
     const int32_t n_tiles = c->n_tiles_gen;
-    const int32_t target = c->sm_count * 8;
+    static const int32_t waves = getenv("GSGP_GEN_WAVES") ? std::max(1, atoi(getenv("GSGP_GEN_WAVES"))) : 8;
+    const int32_t target = c->sm_count * waves;
     int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
     groups = std::min(groups, std::max(1, (nk + 31) / 32));
     int32_t ipg = (nk + groups - 1) / groups;
@@ -1083,9 +1084,9 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
     // i; measured slower at config 2 (4 launches: 4 x 0.31 ms vs 0.94 ms, X tiles staged 4 times), so 1 by default.
     int32_t max_sp = 0;
     if (!c->stage_pool) {
-        int nt = 4;
+        // one process per GPU: leave cores for the other ranks' hosts (world_size processes share the box)
+        int nt = std::max(1, std::min(4, (int)std::thread::hardware_concurrency() / (2 * std::max(1, c->cfg.world_size))));
         if (const char *e = getenv("GSGP_STAGE_THREADS")) nt = std::max(1, std::min(16, atoi(e)));
-        nt = std::max(1, std::min<int>(nt, (int)std::thread::hardware_concurrency()));
         c->stage_pool.reset(new StagePool(nt));
     }
     std::vector<StagePool::Job> &jobs = c->stage_pool->jobs();
