@@ -18,6 +18,7 @@ OP_INIT, OP_XO, OP_MUT, OP_REPR = 0, 1, 2, 3
 RNG_HOST_REPLAY, RNG_DEVICE_PHILOX = 0, 1
 FLAG_KEEP_TREE_SEMANTICS = 1
 FLAG_LINEAR_SCALING = 2
+FLAG_KEEP_RUN_HISTORY = 4
 K_INTERP, K_GSOP, K_FINALIZE, K_PLAN = 0, 1, 2, 3
 
 
@@ -71,6 +72,8 @@ SIGNATURES = {
     "gsgp_get_plan": (C.c_int, [_vp, _vp]),
     "gsgp_get_tree": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, C.c_int32, _ip]),
     "gsgp_get_history": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, _ip]),
+    "gsgp_get_best_semantic_of": (C.c_int, [_vp, C.c_int32, _dp]),
+    "gsgp_get_plan_of": (C.c_int, [_vp, C.c_int32, _vp]),
     "gsgp_generation_index": (C.c_int32, [_vp]),
     "gsgp_eval_trees": (C.c_int, [_vp, C.c_int32, _ip, C.c_int32, _ip, _ip, _dp]),
     "gsgp_set_fitness": (C.c_int, [_vp, _dp, _dp]),

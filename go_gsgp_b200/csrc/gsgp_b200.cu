@@ -176,6 +176,7 @@ private:
 }  // namespace
 
 constexpr int kDrawSets = 3;
+constexpr int kRunHistBlock = 64;
 
 struct gsgp_ctx {
     gsgp_config cfg{};
@@ -225,6 +226,10 @@ struct gsgp_ctx {
     int sm_count = 148;
     int32_t *dindex_best = nullptr;
     BestRec *dhist = nullptr; int32_t hist_cap = 0;
+    // GSGP_FLAG_KEEP_RUN_HISTORY: per generation, in blocks of kRunHistBlock generations
+    bool keep_run = false;
+    std::vector<double *> run_sem;                            // [block] -> kRunHistBlock rows of n_pad doubles
+    std::vector<gsgp_plan_entry *> run_plan;                  // [block] -> kRunHistBlock plans of P entries
 
     PinnedBuf<gsgp_plan_entry> hplan;
     PinnedBuf<Ins> hprog;
@@ -488,13 +493,37 @@ int ensure_hist(gsgp_ctx *c, int32_t gen)
     return 0;
 }
 
+int ensure_run_history(gsgp_ctx *c, int32_t gen)
+{
+    while ((int32_t)c->run_sem.size() * kRunHistBlock <= gen) {
+        double *s = nullptr; gsgp_plan_entry *p = nullptr;
+        CU(c, cudaMalloc((void **)&s, sizeof(double) * (size_t)kRunHistBlock * c->L.n_pad));
+        CU(c, cudaMalloc((void **)&p, sizeof(gsgp_plan_entry) * (size_t)kRunHistBlock * c->cfg.population_size));
+        c->run_sem.push_back(s); c->run_plan.push_back(p);
+    }
+    return 0;
+}
+
 int launch_best(gsgp_ctx *c, int buf, int32_t gen)
 {
     if (ensure_hist(c, gen)) return 1;
-    ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
-    best_kernel<<<1, 1024, 0, c->stream>>>(c->dfit[buf], c->dfit_test[buf], c->cfg.population_size,
-                                           c->cfg.minimization_problem, c->dindex_best, c->dhist + gen);
-    CU(c, cudaGetLastError());
+    {
+        ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+        best_kernel<<<1, 1024, 0, c->stream>>>(c->dfit[buf], c->dfit_test[buf], c->cfg.population_size,
+                                               c->cfg.minimization_problem, c->dindex_best, c->dhist + gen);
+        CU(c, cudaGetLastError());
+    }
+    if (c->keep_run) {                                        // best-of-generation semantic + this generation's decisions
+        if (ensure_run_history(c, gen)) return 1;
+        double *dst = c->run_sem[(size_t)gen / kRunHistBlock] + (size_t)(gen % kRunHistBlock) * c->L.n_pad;
+        ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+        copy_best_row_kernel<<<std::min(1024, (c->L.n_pad / 2 + 255) / 256), 256, 0, c->stream>>>(c->dsem[buf], c->L.n_pad, c->L.n_pad,
+                                                                                                  c->dindex_best, dst);
+        CU(c, cudaGetLastError());
+        if (gen > 0)
+            CU(c, cudaMemcpyAsync(c->run_plan[(size_t)gen / kRunHistBlock] + (size_t)(gen % kRunHistBlock) * c->cfg.population_size,
+                                  c->dplan, sizeof(gsgp_plan_entry) * (size_t)c->cfg.population_size, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return 0;
 }
 
@@ -729,6 +758,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         CUC(cudaFuncSetAttribute(gen_kernel<GSGP_SUMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(plan_draw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         c->linsc = (cfg->flags & GSGP_FLAG_LINEAR_SCALING) != 0;
+        c->keep_run = (cfg->flags & GSGP_FLAG_KEEP_RUN_HISTORY) != 0;
         // pipeline: fused (one gen_kernel launch per generation, R stays on chip) unless the dataset's columns
         // do not fit shared memory, the caller wants R kept (proto dump), or GSGP_PIPELINE=unfused
         const char *pl = getenv("GSGP_PIPELINE");
@@ -845,6 +875,8 @@ void gsgp_destroy(gsgp_ctx *c)
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaFree(c->dplan); cudaFree(c->dprog_off);
     cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
+    for (double *p : c->run_sem) cudaFree(p);
+    for (gsgp_plan_entry *p : c->run_plan) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1254,6 +1286,28 @@ int gsgp_get_history(gsgp_ctx *c, int32_t first, int32_t n, double *best_fit, do
 }
 
 int32_t gsgp_generation_index(const gsgp_ctx *c) { return c ? c->generation : -1; }
+
+int gsgp_get_best_semantic_of(gsgp_ctx *c, int32_t generation, double *out)
+{
+    if (check_ready(c)) return 1;
+    if (!c->keep_run) return fail(c, "context created without GSGP_FLAG_KEEP_RUN_HISTORY");
+    if (generation < 0 || generation > c->generation || (size_t)generation / kRunHistBlock >= c->run_sem.size())
+        return fail(c, "generation %d is not in the run history", generation);
+    return copy_row_out(c, c->run_sem[(size_t)generation / kRunHistBlock] + (size_t)(generation % kRunHistBlock) * c->L.n_pad, out);
+}
+
+int gsgp_get_plan_of(gsgp_ctx *c, int32_t generation, gsgp_plan_entry *plan_out)
+{
+    if (check_ready(c)) return 1;
+    if (!c->keep_run) return fail(c, "context created without GSGP_FLAG_KEEP_RUN_HISTORY");
+    if (generation < 1 || generation > c->generation || (size_t)generation / kRunHistBlock >= c->run_plan.size())
+        return fail(c, "generation %d is not in the run history", generation);
+    const size_t P = (size_t)c->cfg.population_size;
+    CU(c, cudaMemcpyAsync(plan_out, c->run_plan[(size_t)generation / kRunHistBlock] + (size_t)(generation % kRunHistBlock) * P,
+                          sizeof(gsgp_plan_entry) * P, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 int gsgp_set_fitness(gsgp_ctx *c, const double *fit, const double *fit_test)
 {

@@ -194,6 +194,16 @@ class Engine:
         self._ck(self.L.gsgp_get_history(self.h, first, n, capi.dptr(bf), capi.dptr(bt), capi.iptr(bi)))
         return bf, bt, bi
 
+    def get_best_semantic_of(self, generation):
+        out = np.empty(self.n_local)
+        self._ck(self.L.gsgp_get_best_semantic_of(self.h, generation, capi.dptr(out)))
+        return out
+
+    def get_plan_of(self, generation):
+        plan = np.zeros(self.P, PLAN_DTYPE)
+        self._ck(self.L.gsgp_get_plan_of(self.h, generation, plan.ctypes.data))
+        return plan
+
     @property
     def generation_index(self):
         return self.L.gsgp_generation_index(self.h)

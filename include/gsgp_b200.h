@@ -62,7 +62,10 @@ typedef struct {
 } gsgp_config;
 
 enum { GSGP_FLAG_KEEP_TREE_SEMANTICS = 1, /* keep R of the whole last generation (proto dump)                  */
-       GSGP_FLAG_LINEAR_SCALING = 2       /* -linsc: fitness on a + b*semantic (main_cpu.go:181,991-1104,1142-1177) */ };
+       GSGP_FLAG_LINEAR_SCALING = 2,      /* -linsc: fitness on a + b*semantic (main_cpu.go:181,991-1104,1142-1177) */
+       GSGP_FLAG_KEEP_RUN_HISTORY = 4     /* keep, per generation, the decisions and the best individual's semantic on the
+                                             device, so that gsgp_run_generations(n) loses none of the reference's
+                                             per-generation outputs (semantic lines :1499-1500, contributions :885,:1503) */ };
 
 /* One entry per individual per generation: the decisions of the sequential driver loop
  * (main_cpu.go:1447-1470).  In host-replay mode the host fills it; in device mode the selection
@@ -142,6 +145,10 @@ int gsgp_get_tree(gsgp_ctx *ctx, int32_t ind, int32_t which, int32_t *out, int32
 int gsgp_get_history(gsgp_ctx *ctx, int32_t first, int32_t n, double *best_fit, double *best_fit_test,
                      int32_t *best_index);
 int32_t gsgp_generation_index(const gsgp_ctx *ctx);
+/* with GSGP_FLAG_KEEP_RUN_HISTORY: the best individual's semantic (local shard, layout of gsgp_get_semantic) and the
+ * decisions of any past generation (0 = initial population: semantic only) */
+int gsgp_get_best_semantic_of(gsgp_ctx *ctx, int32_t generation, double *out);
+int gsgp_get_plan_of(gsgp_ctx *ctx, int32_t generation, gsgp_plan_entry *plan_out);
 
 /* ---- primitives (parity tests; also usable by operators_effects-style hosts) ------------------ */
 /* semantic_evaluate_array (main_cpu.go:797-827) for n trees; out = n x (nrow_local+nrow_test_local) */

@@ -586,3 +586,34 @@ def test_runs_are_bit_reproducible():
     u = hist["unfused"][0]
     assert np.array_equal(a[2], u[2])                                   # same best individuals
     assert_close(a[3], u[3], 1e-12, "fused vs unfused fitness")
+
+
+def test_run_history_keeps_every_generations_outputs():
+    """GSGP_FLAG_KEEP_RUN_HISTORY: n generations in one asynchronous call lose none of the reference's per-generation
+    outputs -- best-of-generation semantic (main_cpu.go:1499-1500) and the parents for the contributions (:885).
+    Checked bit for bit against a second context stepped one generation at a time (runs are bit-reproducible), and
+    against the oracle for the first generations (later ones can legitimately part ways on near-tied fitness)."""
+    g = _engine_mod()
+    from go_gsgp_b200 import capi
+    X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
+    G = 70                                                     # crosses a history block boundary (64)
+    o, e, _ = _mk(X, y, nrow, population_size=50, seed=9, rng_kind=ob.RNG_PHILOX, flags=capi.FLAG_KEEP_RUN_HISTORY)
+    o2, e2, (fit, fit_test, best) = _mk(X, y, nrow, population_size=50, seed=9, rng_kind=ob.RNG_PHILOX)
+    e.run_generations(G)                                       # one call, no host involvement in between
+    bf, bt, bi = e.get_history(0, G + 1)
+    np.testing.assert_array_equal(e.get_best_semantic_of(0), e2.get_semantic(best))
+    for gen in range(1, G + 1):
+        o.generation() if gen <= 8 else None
+        e2.run_generations(1)
+        fit, fit_test, best = e2.get_fitness()
+        assert best == bi[gen]
+        np.testing.assert_array_equal(e.get_best_semantic_of(gen), e2.get_semantic(best))
+        p, r = e.get_plan_of(gen), e2.get_plan()
+        for k in ("op", "elite", "p1", "p2", "tree0_len", "tree1_len", "ms"):
+            assert np.array_equal(p[k], r[k]), (gen, k)
+        if gen <= 8:
+            assert best == o.index_best
+            assert_close(e.get_best_semantic_of(gen), o.semantic(o.index_best), TOL, f"best semantic of generation {gen}")
+    with pytest.raises(g.GsgpError, match="not in the run history"):
+        e.get_plan_of(G + 1)
+    e.close(); e2.close(); o.close(); o2.close()
