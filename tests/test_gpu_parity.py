@@ -32,7 +32,9 @@ def assert_close(a, b, tol=TOL, what=""):
 
 
 @pytest.mark.parametrize("n,nrow,v,depth,nconst", [
-    (1250, 1000, 5, 6, 0), (1254, 1003, 5, 8, 3), (100, 100, 3, 4, 0), (37, 5, 2, 6, 2), (4099, 2049, 20, 8, 0)])
+    (1250, 1000, 5, 6, 0), (1254, 1003, 5, 8, 3), (100, 100, 3, 4, 0), (37, 5, 2, 6, 2), (4099, 2049, 20, 8, 0),
+    (1301, 1000, 120, 6, 2),      # too wide for shared memory: the unstaged (global-load) interpreter path
+    (777, 500, 40, 7, 1)])
 def test_tree_semantics_bitexact(n, nrow, v, depth, nconst):
     g = _engine_mod()
     X, y, _ = synth_dataset(1, n, v)
@@ -455,6 +457,24 @@ def test_full_size_cfg2_properties_and_spot_parity():
             assert rel_err(nfit_test[k], o.fitness_test(row[nrow:])) <= TOL
     assert nbest == host.best_individual(nfit)
     e.close(); o.close()
+
+
+def test_wide_dataset_falls_back_to_the_unfused_pipeline():
+    """120 variables: the tile's columns do not fit shared memory -> unstaged interpreter + gsop_kernel (no fused kernel)."""
+    X, y, nrow = synth_dataset(5, 2000, 120)
+    for rng_kind in (ob.RNG_ALFG, ob.RNG_PHILOX):
+        o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=40, seed=2, rng_kind=rng_kind, num_random_constants=2)
+        assert best == o.index_best
+        for _ in range(4):
+            o.generation()
+            if rng_kind == ob.RNG_PHILOX:
+                e.run_generations(1); fit, fit_test, best = e.get_fitness()
+            else:
+                fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
+            assert best == o.index_best
+            assert_close(fit, o.fit(), TOL, "fit"); assert_close(fit_test, o.fit_test(), TOL, "fit_test")
+        assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
+        e.close(); o.close()
 
 
 @pytest.mark.parametrize("kw", [
