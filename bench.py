@@ -186,7 +186,10 @@ def main():
 
     from go_gsgp_b200 import Engine, capi, build
     from go_gsgp_b200.host import HostDriver
-    build.build()
+    if rank == 0:
+        build.build()                                       # no-op when the in-tree .so is current
+    if dist is not None:
+        dist.barrier()                                      # one builder: the ranks share the file
 
     w = WORKLOADS[args.workload]
     P, V = w["pop"], w["nvar"]
