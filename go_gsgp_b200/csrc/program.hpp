@@ -1,5 +1,5 @@
 // program.hpp -- the interpreter's program format, shared by the host staging code (trees.hpp) and
-// the on-device random-tree generator (plan_kernel).
+// the on-device random-tree generator (plan_draw_kernel).
 //
 // eval_arrays (main_cpu.go:755-775) recurses over the pointer-prefix array once per fitness case.
 // The device interpreter runs an accumulator program instead: one instruction per FUNCTION node,

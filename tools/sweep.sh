@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: scripts_sweep.sh "<cpt list>" "<tile list>" [extra bench args]
-for cpt in $1; do for tile in $2; do echo "CPT=$cpt TILE=$tile"; GSGP_INTERP_CPT=$cpt GSGP_INTERP_TILE=$tile timeout 180 python bench.py --steps 10 --warmup 3 --no-cpu-baseline $3 2>&1 | python -c "
+for cpt in $1; do for tile in $2; do echo "CPT=$cpt TILE=$tile"; GSGP_INTERP_TILE=$tile timeout 180 python bench.py --steps 10 --warmup 3 --no-cpu-baseline $3 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
