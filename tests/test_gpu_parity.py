@@ -637,3 +637,50 @@ def test_run_history_keeps_every_generations_outputs():
     with pytest.raises(g.GsgpError, match="not in the run history"):
         e.get_plan_of(G + 1)
     e.close(); e2.close(); o.close(); o2.close()
+
+
+@pytest.mark.parametrize("case", range(14))
+def test_randomized_configurations_lockstep(case):
+    """Differential fuzzing: random shapes and settings (seeded), oracle vs CUDA path in lock-step."""
+    rng = np.random.default_rng(1000 + case)
+    v = int(rng.integers(5, 40))
+    nrow = int(rng.integers(1, 3000))
+    nrow_test = int(rng.integers(0, 900))
+    P = int(rng.integers(2, 90))
+    X, y, _ = synth_dataset(7, nrow + nrow_test, v, nrow=nrow)
+    if case % 3 == 0:
+        y = y * 50.0 - 7.0
+    kw = dict(population_size=P, seed=int(rng.integers(1, 1 << 30)),
+              error_measure=int(rng.choice([ob.MSE, ob.RMSE, ob.MAE, ob.MRE])),
+              max_depth_creation=int(rng.integers(1, 10)), tournament_size=int(rng.integers(1, 9)),
+              num_random_constants=int(rng.choice([0, 0, 3, 17])), zero_depth=int(rng.integers(0, 2)),
+              minimization_problem=int(rng.integers(0, 2)), init_type=int(rng.integers(0, 3)),
+              use_linear_scaling=int(rng.integers(0, 2)), n_workers=int(rng.choice([1, 1, 4])),
+              p_crossover=float(rng.choice([0.0, 0.3, 0.6, 1.0])))
+    kw["p_mutation"] = float(min(1.0 - kw["p_crossover"], rng.choice([0.0, 0.3, 0.4, 1.0])))
+    device = bool(rng.integers(0, 2))
+    if device:
+        kw["rng_kind"] = ob.RNG_PHILOX
+        kw["max_depth_creation"] = max(1, min(kw["max_depth_creation"], 9))
+    o, e, (fit, fit_test, best) = _mk(X, y, nrow, **kw)
+    assert best == o.index_best, kw
+    assert_close(fit, o.fit(), TOL, f"initial fit {kw}")
+    for g in range(3):
+        o.generation()
+        if device:
+            e.run_generations(1)
+            fit, fit_test, best = e.get_fitness()
+            p, r = e.get_plan(), o.last_plan()
+            live = r["elite"] == 0
+            assert np.array_equal(p["op"], r["op"]) and np.array_equal(p["p1"][live], r["p1"][live]), (kw, g)
+        else:
+            fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
+        assert_close(fit, o.fit(), TOL, f"fit gen {g} {kw}")
+        assert_close(fit_test, o.fit_test(), TOL, f"fit_test gen {g} {kw}")
+        # the best index can only differ on an exact/near tie of the best fitness
+        if best != o.index_best:
+            assert rel_err(o.fit()[best], o.fit()[o.index_best]) <= 1e-12, (kw, g, best, o.index_best)
+            break
+    else:
+        assert_close(e.get_semantics(), o.semantics(), TOL, f"semantics {kw}")
+    e.close(); o.close()
