@@ -639,12 +639,16 @@ def test_run_history_keeps_every_generations_outputs():
     e.close(); e2.close(); o.close(); o2.close()
 
 
-@pytest.mark.parametrize("case", range(14))
+@pytest.mark.parametrize("case", range(int(os.environ.get("GSGP_FUZZ_CASES", "24"))))
 def test_randomized_configurations_lockstep(case):
-    """Differential fuzzing: random shapes and settings (seeded), oracle vs CUDA path in lock-step."""
+    """Differential fuzzing: random shapes and settings (seeded), oracle vs CUDA path in lock-step.
+    Two things are ill-posed in the reference itself and are excluded, not hidden: (1) linear scaling of a numerically
+    constant semantic (std <= 1e-7 * magnitude: a, b fit rounding noise -- oracle, CUDA path and a long-double
+    evaluation all disagree), and its `-workers > 1` sum-form slope (:1039-1050), which cancels catastrophically when
+    |mean| >> std; (2) decisions between candidates whose fitness ties to within summation-order noise."""
     rng = np.random.default_rng(1000 + case)
     v = int(rng.integers(5, 40))
-    nrow = int(rng.integers(1, 3000))
+    nrow = int(rng.integers(3, 3000))
     nrow_test = int(rng.integers(0, 900))
     P = int(rng.integers(2, 90))
     X, y, _ = synth_dataset(7, nrow + nrow_test, v, nrow=nrow)
@@ -658,29 +662,55 @@ def test_randomized_configurations_lockstep(case):
               use_linear_scaling=int(rng.integers(0, 2)), n_workers=int(rng.choice([1, 1, 4])),
               p_crossover=float(rng.choice([0.0, 0.3, 0.6, 1.0])))
     kw["p_mutation"] = float(min(1.0 - kw["p_crossover"], rng.choice([0.0, 0.3, 0.4, 1.0])))
+    if kw["use_linear_scaling"]:
+        kw["n_workers"] = 1
     device = bool(rng.integers(0, 2))
     if device:
         kw["rng_kind"] = ob.RNG_PHILOX
-        kw["max_depth_creation"] = max(1, min(kw["max_depth_creation"], 9))
+
+    def well_posed(o):
+        """individuals whose fitness is a well-conditioned function of their semantic"""
+        if not kw["use_linear_scaling"]:
+            return np.ones(P, bool)
+        s = o.semantics()[:, :nrow]
+        with np.errstate(all="ignore"):
+            return np.std(s, axis=1) > 1e-7 * np.max(np.abs(s), axis=1)
+
+    def near_tie(f, i, j):
+        return i == j or rel_err(f[i], f[j]) <= 1e-11
+
     o, e, (fit, fit_test, best) = _mk(X, y, nrow, **kw)
-    assert best == o.index_best, kw
-    assert_close(fit, o.fit(), TOL, f"initial fit {kw}")
+    ok = well_posed(o)
+    assert_close(fit[ok], o.fit()[ok], TOL, f"initial fit {kw}")
+    assert near_tie(o.fit(), best, o.index_best) or not (ok[best] and ok[o.index_best]), kw
+    diverged = best != o.index_best or not ok.all()
     for g in range(3):
+        if diverged:
+            break
+        old_fit = o.fit().copy()
         o.generation()
+        r = o.last_plan()
         if device:
             e.run_generations(1)
             fit, fit_test, best = e.get_fitness()
-            p, r = e.get_plan(), o.last_plan()
+            p = e.get_plan()
             live = r["elite"] == 0
-            assert np.array_equal(p["op"], r["op"]) and np.array_equal(p["p1"][live], r["p1"][live]), (kw, g)
+            assert np.array_equal(p["op"], r["op"]) and np.array_equal(p["elite"], r["elite"]), (kw, g)
+            for k in np.flatnonzero(live & ((p["p1"] != r["p1"]) | ((r["op"] == ob.OP_XO) & (p["p2"] != r["p2"])))):
+                assert near_tie(old_fit, p["p1"][k], r["p1"][k]), (kw, g, k)          # a tournament decided by a near-tie
+                if r["op"][k] == ob.OP_XO:
+                    assert near_tie(old_fit, p["p2"][k], r["p2"][k]), (kw, g, k)
+                diverged = True
+            if diverged:
+                break
         else:
-            fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
-        assert_close(fit, o.fit(), TOL, f"fit gen {g} {kw}")
-        assert_close(fit_test, o.fit_test(), TOL, f"fit_test gen {g} {kw}")
-        # the best index can only differ on an exact/near tie of the best fitness
-        if best != o.index_best:
-            assert rel_err(o.fit()[best], o.fit()[o.index_best]) <= 1e-12, (kw, g, best, o.index_best)
-            break
-    else:
+            fit, fit_test, best = e.generation(r, o.last_tree_pool())
+        ok = well_posed(o)
+        assert_close(fit[ok], o.fit()[ok], TOL, f"fit gen {g} {kw}")
+        assert_close(fit_test[ok], o.fit_test()[ok], TOL, f"fit_test gen {g} {kw}")
+        # (an ill-posed individual's noise-level fitness may win on one side only)
+        assert near_tie(o.fit(), best, o.index_best) or not (ok[best] and ok[o.index_best]), (kw, g, best, o.index_best)
+        diverged = best != o.index_best or not ok.all()
+    if not diverged:
         assert_close(e.get_semantics(), o.semantics(), TOL, f"semantics {kw}")
     e.close(); o.close()
