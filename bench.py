@@ -50,6 +50,10 @@ WORKLOADS = {
     # BASELINE.json configs[4] per-GPU share at 8 GPUs with a population that fits one GPU
     "cfg5": dict(cfg_id=5, nvar=20, cases_per_gpu=1_250_000, pop=1000, depth=6, p_xo=0.6, p_mut=0.3,
                  desc="synthetic 20 vars x 1.25M cases per GPU (10M at 8 GPUs), pop 1000"),
+    # BASELINE.json configs[4] at its full population: 10M cases x pop 10,000 at 8 GPUs = 100 GB of semantics per GPU;
+    # two buffers do not fit 180 GB, so the library switches to the single-buffer store (case-block scratch)
+    "cfg5full": dict(cfg_id=5, nvar=20, cases_per_gpu=1_250_000, pop=10_000, depth=6, p_xo=0.6, p_mut=0.3,
+                     desc="synthetic 20 vars x 1.25M cases per GPU (10M at 8 GPUs), pop 10,000, single-buffer store"),
 }
 
 
@@ -249,6 +253,7 @@ def main():
 
     # ---- value: device-RNG mode, resident in HBM ------------------------------------------------
     e, fit, best = setup(capi.RNG_DEVICE_PHILOX)
+    store = {"buffers": e.store_buffers, "buffer_gb": e.store_buffer_bytes / 1e9, "scratch_gb": e.store_scratch_bytes / 1e9}
     stream = torch.cuda.ExternalStream(e.stream)
     e.run_generations(W)
     e.sync()
@@ -275,17 +280,19 @@ def main():
     # ---- the same generations through the unfused pipeline (interp_kernel -> gsop_kernel): the HBM-bound GS
     # kernel on its own, for the roofline target north_star states for it --------------------------------
     Ku = max(3, min(K, 10))
-    e, _, _ = setup(capi.RNG_DEVICE_PHILOX, "unfused")
-    e.run_generations(W)
-    e.sync()
-    e.profile_enable(True)
-    barrier()
-    e.run_generations(Ku)
-    e.sync()
-    barrier()
-    prof_u = {k: e.profile_read(k) for k in (capi.K_INTERP, capi.K_GSOP)}
-    e.profile_enable(False)
-    e.close()
+    prof_u = {capi.K_INTERP: (0, 0.0, 0.0), capi.K_GSOP: (0, 0.0, 0.0)}
+    if store["buffers"] == 2:                                # the unfused pipeline needs the cur/new pair
+        e, _, _ = setup(capi.RNG_DEVICE_PHILOX, "unfused")
+        e.run_generations(W)
+        e.sync()
+        e.profile_enable(True)
+        barrier()
+        e.run_generations(Ku)
+        e.sync()
+        barrier()
+        prof_u = {k: e.profile_read(k) for k in (capi.K_INTERP, capi.K_GSOP)}
+        e.profile_enable(False)
+        e.close()
 
     # ---- e2e: host-replay mode through gsgp_generation() with host buffers -------------------------
     e, fit, best = setup(capi.RNG_HOST_REPLAY)
@@ -373,6 +380,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "global_cases": n_global, "pop": P,
                        "l2": "inputs larger than L2 (semantic store %.2f GB per buffer per GPU)" % (P * n_local * 8 / 1e9),
+                       "store": store,
                        "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building"},

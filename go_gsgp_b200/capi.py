@@ -19,6 +19,7 @@ RNG_HOST_REPLAY, RNG_DEVICE_PHILOX = 0, 1
 FLAG_KEEP_TREE_SEMANTICS = 1
 FLAG_LINEAR_SCALING = 2
 FLAG_KEEP_RUN_HISTORY = 4
+FLAG_SINGLE_BUFFER_STORE = 8
 K_INTERP, K_GSOP, K_FINALIZE, K_PLAN = 0, 1, 2, 3
 
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "gsgp_create": (C.c_int, [C.POINTER(GsgpConfig), C.POINTER(_vp)]),
     "gsgp_destroy": (None, [_vp]),
     "gsgp_local_counts": (C.c_int, [_vp, _ip, _ip]),
+    "gsgp_store_info": (C.c_int, [_vp, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gsgp_set_dataset": (C.c_int, [_vp, _dp]),
     "gsgp_set_dataset_shard": (C.c_int, [_vp, _dp, _dp]),
     "gsgp_set_constants": (C.c_int, [_vp, _dp, C.c_int32]),

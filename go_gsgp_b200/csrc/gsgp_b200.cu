@@ -199,7 +199,14 @@ struct gsgp_ctx {
     bool have_dataset = false, fitness_valid = false;
 
     double *dX = nullptr, *dy = nullptr, *dsym = nullptr;
-    double *dsem[2] = {nullptr, nullptr};
+    double *dsem[2] = {nullptr, nullptr};                     // [P][pitch] each; update_tables flips `cur`
+    // single-buffer store (GSGP_FLAG_SINGLE_BUFFER_STORE, or automatically when two buffers do not fit): ONE allocation
+    // [P][n_pad + shift]; dsem[0] = base, dsem[1] = base + shift.  A generation moves every row by `shift` cases
+    // (alternately right and left), one block of `shift` cases per launch in the order that only ever overwrites
+    // cases whose old values every individual has already consumed.  Memory = (1 + shift/n_pad) x the store, no copies.
+    bool single_store = false;
+    int32_t shift_tiles = 0;                                  // case tiles (256 cases) per block
+    int64_t pitch = 0;                                        // row pitch of the store in doubles
     double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
     double *dR = nullptr;
     double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
@@ -350,7 +357,7 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     if (nk <= 0) return 0;
     GsArgs a{};
     a.plan = c->dplan; a.sem_old = sem_old; a.sem_new = sem_new; a.R = c->dR; a.y = c->dy;
-    a.partial = c->dpartial; a.pitch = c->L.n_pad; a.k0 = k0; a.r_k0 = r_k0; a.n_tiles = c->n_tiles;
+    a.partial = c->dpartial; a.pitch = c->pitch; a.r_pitch = c->L.n_pad; a.k0 = k0; a.r_k0 = r_k0; a.n_tiles = c->n_tiles;
     a.mode = mode; a.L = c->L;
     dim3 grid(c->n_tiles, nk);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
@@ -373,10 +380,11 @@ size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg)
            (1 + kGenWarps) * sizeof(uint64_t) + 16;
 }
 
-int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const double *sem_old, double *sem_new, double bytes)
+int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const double *sem_old, double *sem_new,
+                     int32_t tile_begin, int32_t tile_count, double bytes)
 {
-    if (nk <= 0) return 0;
-    const int32_t n_tiles = c->n_tiles_gen;
+    if (nk <= 0 || tile_count <= 0) return 0;
+    const int32_t n_tiles = tile_count;
     static const int32_t waves = getenv("GSGP_GEN_WAVES") ? std::max(1, atoi(getenv("GSGP_GEN_WAVES"))) : 8;
     const int32_t target = c->sm_count * waves;
     int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
@@ -388,8 +396,8 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
     GenArgs a{};
     a.plan = c->dplan; a.prog_pool = c->ds[c->dcur].prog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->ds[c->dcur].prog_desc;
     a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
-    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->L.n_pad; a.partial = c->dpartial;
-    a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = n_tiles; a.smem_levels = c->gen_levels; a.L = c->L;
+    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin; a.partial = c->dpartial;
+    a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = c->n_tiles_gen; a.smem_levels = c->gen_levels; a.L = c->L;
     const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg);
     dim3 grid(n_tiles, groups);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
@@ -400,6 +408,23 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
     default:       gen_kernel<GSGP_MSE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
     }
     CU(c, cudaGetLastError());
+    return 0;
+}
+
+// one generation's fused launch(es) over individuals [k0, k0+nk): straight into the other store buffer, or -- single-
+// buffer store -- block of cases by block, each launch writing where the previous one has finished reading
+int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const double *sem_old, double *sem_new, double bytes)
+{
+    if (!c->single_store)
+        return launch_gen_tiles(c, k0, nk, slot_k0, sem_old, sem_new, 0, c->n_tiles_gen, bytes);
+    if (k0 != 0 || nk != c->cfg.population_size) return fail(c, "single-buffer store: a generation is one launch sequence");
+    const int32_t nb = (c->n_tiles_gen + c->shift_tiles - 1) / c->shift_tiles;
+    const bool right = sem_new > sem_old;                      // rows move right: last block first (it lands in the free tail)
+    for (int32_t i = 0; i < nb; ++i) {
+        const int32_t b = right ? nb - 1 - i : i;
+        const int32_t t0 = b * c->shift_tiles, nt = std::min(c->shift_tiles, c->n_tiles_gen - t0);
+        if (launch_gen_tiles(c, k0, nk, slot_k0, sem_old, sem_new, t0, nt, bytes * nt / c->n_tiles_gen)) return 1;
+    }
     return 0;
 }
 
@@ -429,7 +454,7 @@ int launch_ls_pass(gsgp_ctx *c, int mode, const double *sem, const double *osum_
     const int P = c->cfg.population_size;
     LsArgs a{};
     a.plan = c->dplan; a.sem = sem; a.y = c->dy; a.partial = c->dpartial; a.osum_all = osum_all; a.ab = c->dab;
-    a.pitch = c->L.n_pad; a.P = P; a.world = c->cfg.world_size; a.n_tiles = c->n_tiles; a.mode = mode;
+    a.pitch = c->pitch; a.P = P; a.world = c->cfg.world_size; a.n_tiles = c->n_tiles; a.mode = mode;
     a.nrow = c->cfg.nrow; a.tbar = c->tbar; a.L = c->L;
     const double n_cases = (double)(c->L.n_tr + c->L.n_te);
     if (P > 65535) return fail(c, "linear scaling supports populations up to 65535");
@@ -517,7 +542,7 @@ int launch_best(gsgp_ctx *c, int buf, int32_t gen)
         if (ensure_run_history(c, gen)) return 1;
         double *dst = c->run_sem[(size_t)gen / kRunHistBlock] + (size_t)(gen % kRunHistBlock) * c->L.n_pad;
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
-        copy_best_row_kernel<<<std::min(1024, (c->L.n_pad / 2 + 255) / 256), 256, 0, c->stream>>>(c->dsem[buf], c->L.n_pad, c->L.n_pad,
+        copy_best_row_kernel<<<std::min(1024, (c->L.n_pad / 2 + 255) / 256), 256, 0, c->stream>>>(c->dsem[buf], c->pitch, c->L.n_pad,
                                                                                                   c->dindex_best, dst);
         CU(c, cudaGetLastError());
         if (gen > 0)
@@ -773,9 +798,33 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMemsetAsync(c->dX, 0, sizeof(double) * row * cfg->nvar, c->stream));
     CUC(cudaMemsetAsync(c->dy, 0, sizeof(double) * row, c->stream));
     CUC(cudaMemsetAsync(c->dsym, 0, sizeof(double) * (size_t)c->n_symbols, c->stream));
+    {   // store (a): two buffers (cur/new), or one buffer + a block of free cases per row when two do not fit (or on request)
+        size_t free_b = 0, total_b = 0;
+        CUC(cudaMemGetInfo(&free_b, &total_b));
+        const size_t store = sizeof(double) * row * P;
+        // everything allocated after the store: tile partials, plan/draw pools, NCCL, the unfused workspace floor
+        const size_t slack = ((size_t)3 << 30) + sizeof(double) * 2 * (size_t)P * std::max(c->n_tiles, c->n_tiles_gen);
+        const bool fits2 = 2 * store + slack <= free_b;
+        c->single_store = c->fused && ((cfg->flags & GSGP_FLAG_SINGLE_BUFFER_STORE) || !fits2);
+        c->pitch = (int64_t)row;
+        if (c->single_store) {
+            const size_t per_tile = sizeof(double) * (size_t)kPass * P;      // bytes of one case tile of every individual
+            size_t spare = free_b > store + slack ? free_b - store - slack : 0;
+            // a block per launch: half the row is plenty (2-3 launches per generation); leave 40 % of the spare memory free
+            int64_t tiles = std::min<int64_t>((int64_t)(spare / 10 * 6 / per_tile), (c->n_tiles_gen + 1) / 2);
+            if (fits2) tiles = std::max<int64_t>(1, c->n_tiles_gen / 4);     // on request: a quarter of the store
+            if (const char *e = getenv("GSGP_SHIFT_TILES")) tiles = atoi(e);
+            if (tiles < 1) { fail(c, "not enough device memory for the semantic store (%.1f GB + one case block)", store / 1e9); return bail(); }
+            c->shift_tiles = (int32_t)std::min<int64_t>(tiles, c->n_tiles_gen);
+            c->pitch = (int64_t)row + (int64_t)c->shift_tiles * kPass;
+        }
+    }
     for (int b = 0; b < 2; ++b) {
-        CUC(cudaMalloc((void **)&c->dsem[b], sizeof(double) * row * P));
-        CUC(cudaMemsetAsync(c->dsem[b], 0, sizeof(double) * row * P, c->stream));
+        if (b == 1 && c->single_store) c->dsem[1] = c->dsem[0] + (size_t)c->shift_tiles * kPass;
+        else {
+            CUC(cudaMalloc((void **)&c->dsem[b], sizeof(double) * (size_t)c->pitch * P));
+            CUC(cudaMemsetAsync(c->dsem[b], 0, sizeof(double) * (size_t)c->pitch * P, c->stream));
+        }
         CUC(cudaMalloc((void **)&c->dfit[b], sizeof(double) * P));
         CUC(cudaMalloc((void **)&c->dfit_test[b], sizeof(double) * P));
         CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * P, c->stream));
@@ -863,6 +912,7 @@ void gsgp_destroy(gsgp_ctx *c)
     if (c->comm) g_nccl.CommDestroy(c->comm);
     for (auto &s : c->prof) for (auto &e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dsym);
+    if (c->single_store) c->dsem[1] = nullptr;                        // one allocation
     for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
     cudaFree(c->dsums2); cudaFree(c->dsums_all2); cudaFree(c->dab);
@@ -886,6 +936,15 @@ int gsgp_local_counts(const gsgp_ctx *c, int32_t *nrow_local, int32_t *nrow_test
     if (!c) return 1;
     if (nrow_local) *nrow_local = c->L.n_tr;
     if (nrow_test_local) *nrow_test_local = c->L.n_te;
+    return 0;
+}
+
+int gsgp_store_info(const gsgp_ctx *c, int32_t *buffers, int64_t *buffer_bytes, int64_t *scratch_bytes)
+{
+    if (!c) return 1;
+    if (buffers) *buffers = c->single_store ? 1 : 2;
+    if (buffer_bytes) *buffer_bytes = (int64_t)sizeof(double) * c->L.n_pad * c->cfg.population_size;
+    if (scratch_bytes) *scratch_bytes = c->single_store ? (int64_t)sizeof(double) * kPass * c->shift_tiles * c->cfg.population_size : 0;
     return 0;
 }
 
@@ -955,7 +1014,7 @@ int gsgp_seed_semantic(gsgp_ctx *c, int32_t ind, const double *sem)
 {
     if (check_ready(c)) return 1;
     if (ind < 0 || ind >= c->cfg.population_size) return fail(c, "individual %d out of range", ind);
-    double *row = c->dsem[c->cur] + (size_t)ind * c->L.n_pad;
+    double *row = c->dsem[c->cur] + (size_t)ind * c->pitch;
     if (c->L.n_tr)
         CU(c, cudaMemcpyAsync(row, sem + c->tr_lo, sizeof(double) * (size_t)c->L.n_tr, cudaMemcpyHostToDevice, c->stream));
     if (c->L.n_te)
@@ -988,7 +1047,7 @@ int gsgp_seed_semantic_files(gsgp_ctx *c, int32_t first_ind, int32_t n_files, co
                       prc == 1 ? "cannot open semantic file" : prc == 2 ? "Cannot parse semantic value" : "Not enough values when reading semantic file");
             break;
         }
-        double *row = c->dsem[c->cur] + (size_t)(first_ind + i) * c->L.n_pad;
+        double *row = c->dsem[c->cur] + (size_t)(first_ind + i) * c->pitch;
         cudaError_t e = cudaSuccess;
         if (c->L.n_tr) e = cudaMemcpyAsync(row, buf[b].p + c->tr_lo, sizeof(double) * (size_t)c->L.n_tr, cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess && c->L.n_te)
@@ -1028,7 +1087,7 @@ int gsgp_eval_initial(gsgp_ctx *c, int32_t first_ind, int32_t n, const int32_t *
     for (int32_t t = 0; t < n; ++t) if (tree_len[t] <= 0) return fail(c, "individual %d has no tree", first_ind + t);
     c->fitness_valid = false;
     return eval_trees_into(c, n, tree_pool, pool_len, tree_off, tree_len,
-                           c->dsem[c->cur] + (size_t)first_ind * c->L.n_pad, c->L.n_pad);
+                           c->dsem[c->cur] + (size_t)first_ind * c->pitch, c->pitch);
 }
 
 int gsgp_eval_trees(gsgp_ctx *c, int32_t n, const int32_t *tree_pool, int32_t pool_len, const int32_t *tree_off,
@@ -1130,7 +1189,7 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
     c->dcur = 0;
     CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
     static const int32_t env_chunks = getenv("GSGP_REPLAY_CHUNKS") ? atoi(getenv("GSGP_REPLAY_CHUNKS")) : 1;
-    const int32_t n_chunks = (c->fused && P >= 512) ? std::max(1, std::min(env_chunks, 16)) : 1;
+    const int32_t n_chunks = (c->fused && !c->single_store && P >= 512) ? std::max(1, std::min(env_chunks, 16)) : 1;
     const double n_cases = (double)(c->L.n_tr + c->L.n_te);
     size_t base = 0;
     double us_stage = 0.0;
@@ -1229,7 +1288,7 @@ int gsgp_get_semantic(gsgp_ctx *c, int32_t ind, double *out)
 {
     if (check_ready(c)) return 1;
     if (ind < 0 || ind >= c->cfg.population_size) return fail(c, "individual %d out of range", ind);
-    return copy_row_out(c, c->dsem[c->cur] + (size_t)ind * c->L.n_pad, out);
+    return copy_row_out(c, c->dsem[c->cur] + (size_t)ind * c->pitch, out);
 }
 
 int gsgp_get_tree_semantic(gsgp_ctx *c, int32_t ind, int32_t which, double *out)

@@ -64,6 +64,9 @@ class Engine:
         self.nrow_local, self.nrow_test_local = a.value, b.value
         self.n_local = a.value + b.value
         self.n_symbols = 4 + nvar + num_constants
+        nb, bb, sb = C.c_int32(), C.c_int64(), C.c_int64()
+        self.L.gsgp_store_info(self.h, C.byref(nb), C.byref(bb), C.byref(sb))
+        self.store_buffers, self.store_buffer_bytes, self.store_scratch_bytes = nb.value, bb.value, sb.value
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):

@@ -63,9 +63,15 @@ typedef struct {
 
 enum { GSGP_FLAG_KEEP_TREE_SEMANTICS = 1, /* keep R of the whole last generation (proto dump)                  */
        GSGP_FLAG_LINEAR_SCALING = 2,      /* -linsc: fitness on a + b*semantic (main_cpu.go:181,991-1104,1142-1177) */
-       GSGP_FLAG_KEEP_RUN_HISTORY = 4     /* keep, per generation, the decisions and the best individual's semantic on the
+       GSGP_FLAG_KEEP_RUN_HISTORY = 4,    /* keep, per generation, the decisions and the best individual's semantic on the
                                              device, so that gsgp_run_generations(n) loses none of the reference's
-                                             per-generation outputs (semantic lines :1499-1500, contributions :885,:1503) */ };
+                                             per-generation outputs (semantic lines :1499-1500, contributions :885,:1503) */
+       GSGP_FLAG_SINGLE_BUFFER_STORE = 8  /* one semantic store instead of main_cpu.go's cur/new pair (:205-228,1191-1197):
+                                             rows are [cases | one free block of cases]; a generation is computed block by
+                                             block, each child block written where the previous block has been consumed,
+                                             so the rows shift by one block per generation (alternately right and left).
+                                             Chosen automatically when two buffers do not fit the device (config 5: 10M
+                                             cases x pop 10,000 on 8 GPUs = 100 GB of semantics per GPU) */ };
 
 /* One entry per individual per generation: the decisions of the sequential driver loop
  * (main_cpu.go:1447-1470).  In host-replay mode the host fills it; in device mode the selection
@@ -90,6 +96,9 @@ void gsgp_shard_range(int32_t n, int32_t rank, int32_t world, int32_t *lo, int32
 int  gsgp_create(const gsgp_config *cfg, gsgp_ctx **out);
 void gsgp_destroy(gsgp_ctx *ctx);
 int  gsgp_local_counts(const gsgp_ctx *ctx, int32_t *nrow_local, int32_t *nrow_test_local);
+/* how the semantic store (init_tables :1257-1284) was laid out: buffers = 2 (cur/new) or 1 (single-buffer store),
+ * bytes per buffer, bytes of the free case block the single buffer carries (0 with two buffers) */
+int  gsgp_store_info(const gsgp_ctx *ctx, int32_t *buffers, int64_t *buffer_bytes, int64_t *scratch_bytes);
 
 /* ---- inputs -------------------------------------------------------------------------------- */
 /* the in-memory `set` built by read_input_data (main_cpu.go:381-421): row-major

@@ -608,6 +608,45 @@ def test_runs_are_bit_reproducible():
     assert_close(a[3], u[3], 1e-12, "fused vs unfused fitness")
 
 
+@pytest.mark.parametrize("shift_tiles", ["1", "3", "5", None])
+def test_single_buffer_store_is_bit_identical_to_two_buffers(shift_tiles):
+    """GSGP_FLAG_SINGLE_BUFFER_STORE (config 5 at its full population: two buffers do not fit): the generation is
+    computed block of cases by block, each launch writing where the previous one has finished reading, so the rows
+    shift by one block per generation (right, then left).  Same kernel, same sums:
+    fitness, best and every semantic must be BIT-identical to the two-buffer store, in both RNG modes, with linear
+    scaling, and against the oracle in lock step."""
+    g = _engine_mod()
+    X, y, nrow = synth_dataset(2, 1900, 6)                              # 8 case tiles of 256
+    if shift_tiles is None:
+        os.environ.pop("GSGP_SHIFT_TILES", None)
+    else:
+        os.environ["GSGP_SHIFT_TILES"] = shift_tiles
+    try:
+        for linsc in (0, 1):
+            runs = []
+            for flags in (0, g.capi.FLAG_SINGLE_BUFFER_STORE | g.capi.FLAG_KEEP_RUN_HISTORY):
+                o, e, _ = _mk(X, y, nrow, population_size=120, seed=5, rng_kind=ob.RNG_PHILOX, flags=flags,
+                              use_linear_scaling=linsc)
+                assert e.store_buffers == (1 if flags else 2)
+                assert (e.store_scratch_bytes > 0) == bool(flags)
+                e.run_generations(9)
+                fit, fit_test, best = e.get_fitness()
+                runs.append((fit, fit_test, best, e.get_semantics()))
+                e.close(); o.close()
+            (f0, t0, b0, s0), (f1, t1, b1, s1) = runs
+            np.testing.assert_array_equal(f0, f1); np.testing.assert_array_equal(t0, t1)
+            assert b0 == b1
+            np.testing.assert_array_equal(s0, s1)
+        # host replay, lock step with the oracle
+        o, e, _ = _mk(X, y, nrow, population_size=60, seed=8, flags=g.capi.FLAG_SINGLE_BUFFER_STORE)
+        assert e.store_buffers == 1
+        _lockstep_replay(o, e, 8)
+        assert_close(e.get_semantics(), o.semantics(), TOL, "single-buffer store semantics")
+        e.close(); o.close()
+    finally:
+        os.environ.pop("GSGP_SHIFT_TILES", None)
+
+
 def test_run_history_keeps_every_generations_outputs():
     """GSGP_FLAG_KEEP_RUN_HISTORY: n generations in one asynchronous call lose none of the reference's per-generation
     outputs -- best-of-generation semantic (main_cpu.go:1499-1500) and the parents for the contributions (:885).
