@@ -30,7 +30,8 @@ namespace gsgp {
 enum { A_ADD = 0, A_SUB = 1, A_MUL = 2, A_DIV = 3, A_RSUB = 4, A_RDIV = 5, A_MOV = 6 };
 enum { K_LOADA = 8, K_PUSH = 16, K_POP = 32 };
 
-struct Ins { uint32_t code;  /* level << 8 | K_* flags | aop */  uint32_t ab;  /* a | b << 16 */ };
+constexpr int kLevelShift = 11;                         // spill level pre-scaled to its byte offset: levels are 256 cases x 8 B apart
+struct Ins { uint32_t code;  /* level << kLevelShift | K_* flags | aop */  uint32_t ab;  /* a | b << 16 */ };
 
 // per tree-slot descriptor word: instruction count | spill levels needed << 24
 GSGP_HD int32_t prog_desc(int n_ins, int stack_need) { return n_ins | (stack_need << 24); }
@@ -102,7 +103,7 @@ GSGP_HD bool compile_postfix(PostA post, int len, Ins *out, int &n_out, int &sta
             if (lt && rt) {
                 code = K_LOADA | tok;
                 if (f.live) {                           // a pending sibling value lives in acc: spill it
-                    code |= K_PUSH | ((uint32_t)spills << 8);
+                    code |= K_PUSH | ((uint32_t)spills << kLevelShift);
                     if (++spills > stack_need) stack_need = spills;
                 }
                 ab = (uint32_t)(post[l] - 4u) | ((uint32_t)(post[r] - 4u) << 16);
@@ -130,7 +131,7 @@ GSGP_HD bool compile_postfix(PostA post, int len, Ins *out, int &n_out, int &sta
             continue;
         } else {                                        // popped value = the child evaluated first
             --spills;
-            code = K_POP | ((uint32_t)spills << 8) | (f.first_is_left ? rev : tok);
+            code = K_POP | ((uint32_t)spills << kLevelShift) | (f.first_is_left ? rev : tok);
         }
         out[n_out].code = code;
         out[n_out].ab = ab;

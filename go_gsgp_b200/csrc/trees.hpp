@@ -132,7 +132,7 @@ inline bool compile_prefix_tree(const int32_t *tree, int32_t len, int32_t n_symb
             if (lt && rt) {
                 code = K_LOADA | tok;
                 if (f.live) {
-                    code |= K_PUSH | ((uint32_t)spills << 8);
+                    code |= K_PUSH | ((uint32_t)spills << kLevelShift);
                     if (++spills > stack_need) stack_need = spills;
                 }
                 ab = (uint32_t)(tree[l] - kNumFunc) | ((uint32_t)(tree[r] - kNumFunc) << 16);
@@ -154,7 +154,7 @@ inline bool compile_prefix_tree(const int32_t *tree, int32_t len, int32_t n_symb
             continue;
         } else {
             --spills;
-            code = K_POP | ((uint32_t)spills << 8) | (f.first_is_left ? rev : tok);
+            code = K_POP | ((uint32_t)spills << kLevelShift) | (f.first_is_left ? rev : tok);
         }
         out[n_out].code = code;
         out[n_out].ab = ab;

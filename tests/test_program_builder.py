@@ -30,7 +30,7 @@ def run_program(code, ab, cols):
     stack = {}
     with np.errstate(all="ignore"):
         for c, w in zip(code.tolist(), ab.tolist()):
-            level, aop = c >> 8, c & 7
+            level, aop = c >> 11, c & 7                      # program.hpp kLevelShift
             if c & K_PUSH:
                 stack[level] = acc.copy()
             if c & K_LOADA:
@@ -94,7 +94,7 @@ def test_programs_reproduce_oracle_tree_semantics(depth, nconst, zero_depth):
         out = run_program(code, ab, cols)
         ref = o.semantic_evaluate_array(tree)
         assert same_bits(out, ref)
-        levels = [c >> 8 for c in code.tolist() if c & (K_PUSH | K_POP)]
+        levels = [c >> 11 for c in code.tolist() if c & (K_PUSH | K_POP)]
         assert all(l < need for l in levels)
         needs.append(need)
     o.close()
