@@ -205,6 +205,7 @@ struct gsgp_ctx {
     // (alternately right and left), one block of `shift` cases per launch in the order that only ever overwrites
     // cases whose old values every individual has already consumed.  Memory = (1 + shift/n_pad) x the store, no copies.
     bool single_store = false;
+    int32_t gen_warps = kGenWarpsDefault;                         // warps per gen_kernel block
     int32_t shift_tiles = 0;                                  // case tiles (256 cases) per block
     int64_t pitch = 0;                                        // row pitch of the store in doubles
     double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
@@ -372,12 +373,18 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
 }
 
 // fused pipeline: shared memory of one gen_kernel block for `ipg` individuals per group
-size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg)
+size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps)
 {
     const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
-    const size_t per_warp = ((size_t)(levels + 2) * kPass + 2 * 2 * kProgSmem) * sizeof(double);
-    return (ncol + 1) * kPass * sizeof(double) + per_warp * kGenWarps + (size_t)ipg * sizeof(GenSlot) +
-           (1 + kGenWarps) * sizeof(uint64_t) + 16;
+    const size_t per_warp = ((size_t)(levels + 2) * kPass + 2 * 2 * kGenProgSmem) * sizeof(double);
+    return (ncol + 1) * kPass * sizeof(double) + per_warp * warps + (size_t)ipg * sizeof(GenSlot) +
+           (1 + warps) * sizeof(uint64_t) + 16;
+}
+
+template <int MEASURE>
+void launch_gen_kernel(gsgp_ctx *c, dim3 grid, size_t smem, const GenArgs &a)
+{
+    gen_kernel<MEASURE, kGenWarpsDefault><<<grid, kGenWarpsDefault * 32, smem, c->stream>>>(a);
 }
 
 int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const double *sem_old, double *sem_new,
@@ -390,7 +397,7 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
     int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
     groups = std::min(groups, std::max(1, (nk + 31) / 32));
     int32_t ipg = (nk + groups - 1) / groups;
-    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
+    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
     groups = (nk + ipg - 1) / ipg;
     if (groups > 65535) return fail(c, "population chunk too large for one launch");
     GenArgs a{};
@@ -398,14 +405,14 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
     a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
     a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin; a.partial = c->dpartial;
     a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = c->n_tiles_gen; a.smem_levels = c->gen_levels; a.L = c->L;
-    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg);
+    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps);
     dim3 grid(n_tiles, groups);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
     switch (c->linsc ? GSGP_SUMO : c->cfg.error_measure) {
-    case GSGP_SUMO: gen_kernel<GSGP_SUMO><<<grid, kGenThreads, smem, c->stream>>>(a); break;
-    case GSGP_MAE: gen_kernel<GSGP_MAE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
-    case GSGP_MRE: gen_kernel<GSGP_MRE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
-    default:       gen_kernel<GSGP_MSE><<<grid, kGenThreads, smem, c->stream>>>(a); break;
+    case GSGP_SUMO: launch_gen_kernel<GSGP_SUMO>(c, grid, smem, a); break;
+    case GSGP_MAE: launch_gen_kernel<GSGP_MAE>(c, grid, smem, a); break;
+    case GSGP_MRE: launch_gen_kernel<GSGP_MRE>(c, grid, smem, a); break;
+    default:       launch_gen_kernel<GSGP_MSE>(c, grid, smem, a); break;
     }
     CU(c, cudaGetLastError());
     return 0;
@@ -777,10 +784,10 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         const int kMaxSmem = 227 * 1024;
         CUC(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_SUMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MSE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MAE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MRE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_SUMO, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(plan_draw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         c->linsc = (cfg->flags & GSGP_FLAG_LINEAR_SCALING) != 0;
         c->keep_run = (cfg->flags & GSGP_FLAG_KEEP_RUN_HISTORY) != 0;
@@ -789,7 +796,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         const char *pl = getenv("GSGP_PIPELINE");
         c->gen_levels = 2;
         c->fused = !(cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) && !(pl && strcmp(pl, "unfused") == 0) &&
-                   gen_smem_bytes(c, c->gen_levels, 32) <= (size_t)kMaxSmem;
+                   gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps) <= (size_t)kMaxSmem;
     }
     // +256 doubles of slack: the unstaged multi-pair path may read (never use) past the last tile
     CUC(cudaMalloc((void **)&c->dX, sizeof(double) * (row * cfg->nvar + 256)));

@@ -88,6 +88,60 @@ def test_deep_tree_uses_local_stack():
     np.testing.assert_array_equal(got, o.semantic_evaluate_array(t))
 
 
+def _random_tree_array(rng, depth, nvar, full=True):
+    """pointer-prefix array of create_grow_tree_arrays' format (main_cpu.go:609-639): [op, i1, i2, <child1>, <child2>]"""
+    out = []
+
+    def rec(d):
+        pos = len(out)
+        if d == 0 or (not full and d < depth and rng.random() < 0.3):
+            out.append(4 + int(rng.integers(nvar)))
+            return
+        out.extend([int(rng.integers(4)), 0, 0])
+        out[pos + 1] = len(out); rec(d - 1)
+        out[pos + 2] = len(out); rec(d - 1)
+    rec(depth)
+    return np.array(out, np.int32)
+
+
+@pytest.mark.parametrize("depth,full", [(6, True), (7, True), (8, True), (9, False)])
+def test_fused_path_runs_long_programs_in_chunks(depth, full):
+    """gen_kernel stages a program 32 instructions at a time; trees with more function nodes than that (up to 255 here)
+    run chunk by chunk with the accumulator and the spill stack carried across.  The children must match the oracle;
+    trees whose spill need exceeds the shared-memory levels take the generic path inside the same kernel."""
+    g = _engine_mod()
+    rng = np.random.default_rng(100 + depth)
+    V, N, nrow, P = 6, 1500, 1100, 8
+    X, y, _ = synth_dataset(3, N, V)
+    trees = [_random_tree_array(rng, depth, V, full) for _ in range(2 * P)]
+    off = np.cumsum([0] + [len(t) for t in trees])
+    pool = np.concatenate(trees).astype(np.int32)
+    cfg = ob.make_config(population_size=P, error_measure=ob.RMSE)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    e = g.Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=ob.RMSE)
+    e.set_dataset(X, y); e.set_constants(o.symbol_values())
+    seeds = [rng.normal(size=N) for _ in range(P)]
+    for i, sem in enumerate(seeds):
+        o.seed_semantic(i, sem); e.seed_semantic(i, sem)
+    o.initialize_population(P); o.evaluate(); e.fitness_all()
+    plan = np.zeros(P, ob.PLAN_DTYPE)
+    for k in range(P):
+        t0, t1 = 2 * k, 2 * k + 1
+        if k % 2 == 0:
+            plan[k] = (ob.OP_XO, 0, (k + 1) % P, (k + 3) % P, off[t0], len(trees[t0]), -1, 0, 0.0)
+        else:
+            plan[k] = (ob.OP_MUT, 0, (k + 2) % P, 0, off[t0], len(trees[t0]), off[t1], len(trees[t1]), 0.37)
+    o.generation_replay(plan, pool)
+    fit, fit_test, best = e.generation(plan, pool)
+    assert_close(e.get_semantics(), o.semantics(), TOL, "children of long programs")
+    assert_close(fit, o.fit(), TOL, "fit"); assert_close(fit_test, o.fit_test(), TOL, "fit_test")
+    assert best == o.index_best
+    for t in trees[:4]:                                                # and the trees alone, bit for bit (unfused interpreter)
+        np.testing.assert_array_equal(e.eval_trees([t])[0], o.semantic_evaluate_array(t))
+    e.close(); o.close()
+
+
 @pytest.mark.parametrize("measure", [ob.MSE, ob.RMSE, ob.MAE, ob.MRE])
 def test_initial_evaluate(measure):
     X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)
