@@ -254,6 +254,7 @@ def main():
     # ---- value: device-RNG mode, resident in HBM ------------------------------------------------
     e, fit, best = setup(capi.RNG_DEVICE_PHILOX)
     store = {"buffers": e.store_buffers, "buffer_gb": e.store_buffer_bytes / 1e9, "scratch_gb": e.store_scratch_bytes / 1e9}
+    exchange = e.exchange
     stream = torch.cuda.ExternalStream(e.stream)
     e.run_generations(W)
     e.sync()
@@ -380,7 +381,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "global_cases": n_global, "pop": P,
                        "l2": "inputs larger than L2 (semantic store %.2f GB per buffer per GPU)" % (P * n_local * 8 / 1e9),
-                       "store": store,
+                       "store": store, "exchange": exchange,
                        "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building"},

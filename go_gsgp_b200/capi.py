@@ -58,6 +58,7 @@ SIGNATURES = {
     "gsgp_destroy": (None, [_vp]),
     "gsgp_local_counts": (C.c_int, [_vp, _ip, _ip]),
     "gsgp_store_info": (C.c_int, [_vp, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gsgp_exchange_mode": (C.c_int, [_vp]),
     "gsgp_set_dataset": (C.c_int, [_vp, _dp]),
     "gsgp_set_dataset_shard": (C.c_int, [_vp, _dp, _dp]),
     "gsgp_set_constants": (C.c_int, [_vp, _dp, C.c_int32]),

@@ -254,6 +254,15 @@ struct gsgp_ctx {
     std::vector<gsgp_plan_entry> last_plan;
 
     ncclComm_t comm = nullptr;
+    // peer exchange of the partial sums (kernels.cuh, reduce_partials_kernel): CUDA IPC mappings of every rank's
+    // receive buffer; falls back to ncclAllGather when the mappings cannot be opened (or GSGP_EXCHANGE=nccl)
+    bool p2p = false;
+    unsigned char *xbase = nullptr;                           // local: [kXchgSlots][world][2P] doubles | flags | counter | err
+    void *xpeer_base[kMaxPeers] = {};                         // opened mappings of the peers' xbase
+    XchgDev xdev{};
+    size_t xflags_off = 0;
+    int32_t *xerr = nullptr;
+    unsigned long long xseq = 0;
     ProfSlot prof[GSGP_K_COUNT];
     int profiling = 0;                                        // 0 off, 1 generation kernels only, 2 every kernel
     int64_t launch_count = 0;
@@ -440,18 +449,104 @@ int launch_gen(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const doubl
 int reduce_and_gather(gsgp_ctx *c, int mode, int32_t n_tiles, double *local, double *gathered, const double **all)
 {
     const int P = c->cfg.population_size;
+    const int W = c->cfg.world_size;
+    ReduceArgs r{c->dplan, c->dpartial, local, P, n_tiles, mode, XchgDev{}};
+    if (c->p2p) {                                                      // fused: sums go straight into every peer's slot
+        r.x = c->xdev;
+        r.x.seq = ++c->xseq;
+        r.x.slot = (int32_t)(c->xseq % kXchgSlots);
+    }
     {
-        ReduceArgs r{c->dplan, c->dpartial, local, P, n_tiles, mode};
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
         reduce_partials_kernel<<<(P * 32 + 255) / 256, 256, 0, c->stream>>>(r);
         CU(c, cudaGetLastError());
     }
     *all = local;
-    if (c->cfg.world_size > 1) {
+    if (c->p2p) {
+        static const unsigned long long timeout_ns =
+            (unsigned long long)(getenv("GSGP_EXCHANGE_TIMEOUT_MS") ? atof(getenv("GSGP_EXCHANGE_TIMEOUT_MS")) : 20000.0) * 1000000ull;
+        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(c->xbase + c->xflags_off) + (size_t)r.x.slot * W;
+        ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+        xchg_wait_kernel<<<1, 32, 0, c->stream>>>(flags, W, r.x.seq, timeout_ns, c->xerr);
+        CU(c, cudaGetLastError());
+        *all = reinterpret_cast<const double *>(c->xbase) + (size_t)r.x.slot * W * 2 * P;
+    } else if (W > 1) {
         ncclResult_t rc = g_nccl.AllGather(local, gathered, (size_t)2 * P, ncclDouble, c->comm, c->stream);
         if (rc != ncclSuccess) return fail(c, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
         *all = gathered;
     }
+    return 0;
+}
+
+// a byte-wise all-gather through NCCL on the context's stream (setup-time exchanges and barriers)
+int nccl_gather_bytes(gsgp_ctx *c, const void *mine, void *all_host, size_t bytes)
+{
+    const int W = c->cfg.world_size;
+    unsigned char *d = nullptr;
+    CU(c, cudaMalloc((void **)&d, bytes * (W + 1)));
+    CU(c, cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t rc = g_nccl.AllGather(d, d + bytes, bytes, ncclChar, c->comm, c->stream);
+    if (rc != ncclSuccess) { cudaFree(d); return fail(c, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc)); }
+    CU(c, cudaMemcpyAsync(all_host, d + bytes, bytes * W, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return 0;
+}
+
+// maps every rank's receive buffer into this process (CUDA IPC over NVLink peer access).  All ranks agree on the
+// outcome: one rank that cannot open a mapping sends everybody back to the NCCL all-gather.
+int setup_peer_exchange(gsgp_ctx *c)
+{
+    const int W = c->cfg.world_size, P = c->cfg.population_size;
+    const char *ex = getenv("GSGP_EXCHANGE");
+    bool want = W <= kMaxPeers && !(ex && strcmp(ex, "nccl") == 0);
+    const size_t data_bytes = sizeof(double) * kXchgSlots * (size_t)W * 2 * P;
+    c->xflags_off = (data_bytes + 255) / 256 * 256;
+    const size_t flag_bytes = sizeof(unsigned long long) * kXchgSlots * (size_t)W;
+    const size_t ctr_off = c->xflags_off + (flag_bytes + 255) / 256 * 256;
+    const size_t total = ctr_off + 256;
+    cudaIpcMemHandle_t mine{};
+    unsigned char ok = 0;
+    if (want) {
+        CU(c, cudaMalloc((void **)&c->xbase, total));
+        CU(c, cudaMemsetAsync(c->xbase, 0, total, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        ok = cudaIpcGetMemHandle(&mine, c->xbase) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    std::vector<cudaIpcMemHandle_t> handles((size_t)W);
+    if (nccl_gather_bytes(c, &mine, handles.data(), sizeof(mine))) return 1;
+    std::vector<unsigned char> oks((size_t)W);
+    if (nccl_gather_bytes(c, &ok, oks.data(), 1)) return 1;
+    bool all_ok = want;
+    for (unsigned char v : oks) all_ok = all_ok && v;
+    unsigned char opened = all_ok;
+    if (all_ok) {
+        for (int r = 0; r < W && opened; ++r) {
+            if (r == c->cfg.rank) { c->xpeer_base[r] = nullptr; continue; }
+            if (cudaIpcOpenMemHandle(&c->xpeer_base[r], handles[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError(); c->xpeer_base[r] = nullptr; opened = 0;
+            }
+        }
+    }
+    if (nccl_gather_bytes(c, &opened, oks.data(), 1)) return 1;     // also the barrier: every buffer is zeroed and mapped
+    bool use = all_ok;
+    for (unsigned char v : oks) use = use && v;
+    if (!use) {
+        for (int r = 0; r < W; ++r) if (c->xpeer_base[r]) { cudaIpcCloseMemHandle(c->xpeer_base[r]); c->xpeer_base[r] = nullptr; }
+        cudaFree(c->xbase); c->xbase = nullptr;
+        c->p2p = false;
+        return 0;
+    }
+    for (int r = 0; r < W; ++r) {
+        unsigned char *b = r == c->cfg.rank ? c->xbase : static_cast<unsigned char *>(c->xpeer_base[r]);
+        c->xdev.peer_data[r] = reinterpret_cast<double *>(b);
+        c->xdev.peer_flags[r] = reinterpret_cast<unsigned long long *>(b + c->xflags_off);
+    }
+    c->xdev.counter = reinterpret_cast<unsigned int *>(c->xbase + ctr_off);
+    c->xerr = reinterpret_cast<int32_t *>(c->xbase + ctr_off + 64);
+    c->xdev.world = W; c->xdev.rank = c->cfg.rank;
+    c->p2p = true;
     return 0;
 }
 
@@ -904,6 +999,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         ncclUniqueId id; memcpy(&id, cfg->nccl_id, 128);
         ncclResult_t rc = g_nccl.CommInitRank(&c->comm, cfg->world_size, id, cfg->rank);
         if (rc != ncclSuccess) { fail(c, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); return bail(); }
+        if (setup_peer_exchange(c)) return bail();
     }
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
@@ -916,6 +1012,13 @@ void gsgp_destroy(gsgp_ctx *c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->p2p) {                                                      // collective, like the creation: nobody unmaps or frees
+        unsigned char b = 1; std::vector<unsigned char> all((size_t)c->cfg.world_size);   // a buffer a peer may still touch
+        nccl_gather_bytes(c, &b, all.data(), 1);
+        for (int r = 0; r < c->cfg.world_size; ++r) if (c->xpeer_base[r]) cudaIpcCloseMemHandle(c->xpeer_base[r]);
+        nccl_gather_bytes(c, &b, all.data(), 1);
+    }
+    cudaFree(c->xbase);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     for (auto &s : c->prof) for (auto &e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dsym);
@@ -944,6 +1047,12 @@ int gsgp_local_counts(const gsgp_ctx *c, int32_t *nrow_local, int32_t *nrow_test
     if (nrow_local) *nrow_local = c->L.n_tr;
     if (nrow_test_local) *nrow_test_local = c->L.n_te;
     return 0;
+}
+
+int gsgp_exchange_mode(const gsgp_ctx *c)
+{
+    if (!c || c->cfg.world_size <= 1) return 0;
+    return c->p2p ? 2 : 1;
 }
 
 int gsgp_store_info(const gsgp_ctx *c, int32_t *buffers, int64_t *buffer_bytes, int64_t *scratch_bytes)
@@ -1128,7 +1237,10 @@ static int read_fitness(gsgp_ctx *c, double *fit, double *fit_test, int32_t *ind
     if (fit) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
     if (fit_test) CU(c, cudaMemcpyAsync(c->hfit.p + P, c->dfit_test[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
     if (index_best) CU(c, cudaMemcpyAsync(c->hint.p, c->dindex_best, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->hint.p[1] = 0;
+    if (c->p2p) CU(c, cudaMemcpyAsync(c->hint.p + 1, c->xerr, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->hint.p[1]) return fail(c, "peer exchange timed out: a rank did not deliver its partial sums");
     if (fit) memcpy(fit, c->hfit.p, sizeof(double) * P);
     if (fit_test) memcpy(fit_test, c->hfit.p + P, sizeof(double) * P);
     if (index_best) *index_best = c->hint.p[0];

@@ -67,6 +67,7 @@ class Engine:
         nb, bb, sb = C.c_int32(), C.c_int64(), C.c_int64()
         self.L.gsgp_store_info(self.h, C.byref(nb), C.byref(bb), C.byref(sb))
         self.store_buffers, self.store_buffer_bytes, self.store_scratch_bytes = nb.value, bb.value, sb.value
+        self.exchange = {0: "none", 1: "nccl", 2: "p2p"}[self.L.gsgp_exchange_mode(self.h)]
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):

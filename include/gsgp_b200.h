@@ -99,6 +99,9 @@ int  gsgp_local_counts(const gsgp_ctx *ctx, int32_t *nrow_local, int32_t *nrow_t
 /* how the semantic store (init_tables :1257-1284) was laid out: buffers = 2 (cur/new) or 1 (single-buffer store),
  * bytes per buffer, bytes of the free case block the single buffer carries (0 with two buffers) */
 int  gsgp_store_info(const gsgp_ctx *ctx, int32_t *buffers, int64_t *buffer_bytes, int64_t *scratch_bytes);
+/* how the per-generation partial sums travel between ranks: 0 = single GPU, 1 = ncclAllGather, 2 = fused into the
+ * reduction kernel as direct stores into the peers' buffers (CUDA IPC over NVLink; GSGP_EXCHANGE=nccl forces 1) */
+int  gsgp_exchange_mode(const gsgp_ctx *ctx);
 
 /* ---- inputs -------------------------------------------------------------------------------- */
 /* the in-memory `set` built by read_input_data (main_cpu.go:381-421): row-major

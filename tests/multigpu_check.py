@@ -39,6 +39,8 @@ def main():
         e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE, rng_seed=5,
                    rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=fresh_nccl_id(),
                    use_linear_scaling=(mode == capi.RNG_DEVICE_PHILOX))
+        want = os.environ.get("GSGP_EXCHANGE", "p2p")
+        assert e.exchange == want, (e.exchange, want)       # the fused peer exchange is the default; NCCL on request
         e.set_dataset(X, y)
         e.set_constants(o.symbol_values())
         o.initialize_population(0)
@@ -73,7 +75,7 @@ def main():
         e.close(); o.close()
     dist.barrier()
     if rank == 0:
-        print(f"MULTIGPU_OK world={world}")
+        print(f"MULTIGPU_OK world={world} exchange={os.environ.get('GSGP_EXCHANGE', 'p2p')}")
     dist.destroy_process_group()
 
 

@@ -377,8 +377,10 @@ def test_error_behaviour():
 
 
 @pytest.mark.gpu
-def test_multi_gpu_case_sharding_matches_oracle():
-    """N>1: case-sharded engines (NCCL all-gather of the partial sums) against the global oracle."""
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_multi_gpu_case_sharding_matches_oracle(exchange):
+    """N>1: case-sharded engines against the global oracle; the partial sums travel as direct stores into the peers'
+    buffers from the reduction kernel (default) or through ncclAllGather (GSGP_EXCHANGE=nccl)."""
     import subprocess
     import sys
     import torch
@@ -388,8 +390,8 @@ def test_multi_gpu_case_sharding_matches_oracle():
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(os.path.dirname(__file__), "multigpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, GSGP_EXCHANGE=exchange))
+    assert out.returncode == 0 and f"MULTIGPU_OK world={world} exchange={exchange}" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
 def test_sigmoid_accuracy_scan():
