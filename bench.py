@@ -175,6 +175,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly one JSON line: whatever libraries print on fd 1 (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -388,7 +392,7 @@ def main():
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
