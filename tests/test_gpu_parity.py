@@ -53,6 +53,60 @@ def test_tree_semantics_bitexact(n, nrow, v, depth, nconst):
         assert np.array_equal(row, want, equal_nan=True), f"tree {list(t)[:12]}"
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_datasets_full_of_zeros_and_extremes_stay_bit_exact(fused):
+    """Real datasets have binary / integer / sparse columns: zero numerators and zero denominators (protected
+    division, main_cpu.go:736-741), plus subnormal, huge and infinite intermediate values.  Lanes holding such operands
+    leave the interleaved division for the per-lane div.rn.f64 block; tree semantics must stay bit-identical to the
+    oracle (sign of zero included), through the interpreter kernel and through the fused generation kernel."""
+    g = _engine_mod()
+    rng = np.random.default_rng(77)
+    N, V, nrow = 2100, 8, 1500
+    X = np.empty((N, V))
+    X[:, 0] = rng.integers(0, 2, N)                            # binary
+    X[:, 1] = rng.integers(-2, 3, N)                           # small integers with zeros
+    X[:, 2] = rng.choice([0.0, -0.0, 1e-320, -1e-310, 1e300, -1e305, 5e-324, 1.0], N)   # signed zeros, subnormals, huge
+    X[:, 3] = rng.uniform(-1, 1, N) * (rng.random(N) < 0.5)    # sparse
+    X[:, 4] = np.ldexp(rng.uniform(1, 2, N), rng.integers(-1000, 1000, N))
+    X[:, 5:] = rng.uniform(-1, 1, (N, V - 5))
+    y = rng.normal(size=N)
+    cfg = ob.make_config(population_size=6, max_depth_creation=7, rng_seed=3)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    trees = [o.create_grow_tree_arrays() for _ in range(240)]
+    e = g.Engine(population_size=6, nvar=V, nrow=nrow, nrow_test=N - nrow, max_depth_creation=7)
+    e.set_dataset(X, y); e.set_constants(o.symbol_values())
+    if not fused:
+        for t, row in zip(trees, e.eval_trees(trees)):
+            want = o.semantic_evaluate_array(t)
+            assert np.array_equal(row.view(np.int64)[~np.isnan(want)], want.view(np.int64)[~np.isnan(want)]), list(t)[:16]
+            assert np.array_equal(np.isnan(row), np.isnan(want))
+    else:
+        # through gen_kernel: child = 0 + 1*(sigma(R1) - sigma(R2)) and child = sigma(R) pin R up to sigma's rounding
+        P = 6
+        seeds = [np.ones(N), np.zeros(N)] + [rng.normal(size=N) for _ in range(P - 2)]
+        for i, sem in enumerate(seeds):
+            o.seed_semantic(i, sem); e.seed_semantic(i, sem)
+        o.initialize_population(P); o.evaluate(); e.fitness_all()
+        for g0 in range(0, 240, 2 * P):
+            batch = trees[g0:g0 + 2 * P]
+            off = np.cumsum([0] + [len(t) for t in batch])
+            pool = np.concatenate(batch).astype(np.int32)
+            plan = np.zeros(P, ob.PLAN_DTYPE)
+            for k in range(P):
+                if k % 2 == 0:
+                    plan[k] = (ob.OP_XO, 0, 0, 1, off[2 * k], len(batch[2 * k]), -1, 0, 0.0)
+                else:
+                    plan[k] = (ob.OP_MUT, 0, 1, 0, off[2 * k], len(batch[2 * k]), off[2 * k + 1], len(batch[2 * k + 1]), 1.0)
+            o.generation_replay(plan, pool)
+            e.generation(plan, pool)
+            assert_close(e.get_semantics(), o.semantics(), 1e-12, f"children of trees {g0}..")
+            for i, sem in enumerate(seeds):                    # same parents for the next batch
+                o.seed_semantic(i, sem); e.seed_semantic(i, sem)
+            o.evaluate(); e.fitness_all()
+    e.close(); o.close()
+
+
 def test_toy_fixture_kats():
     g = _engine_mod()
     X, y, nrow = toy_fixture()
