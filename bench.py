@@ -346,7 +346,7 @@ def main():
     achieved = local_updates * bpu * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this
     # workload (profiles/README.md); null for workloads that were not captured
-    traffic = {("cfg2", True): 1.756e9, ("cfg2", False): 2.906e9}.get((args.workload, fused)) if world == 1 else None
+    traffic = {("cfg2", True): 1.744e9, ("cfg2", False): 2.895e9}.get((args.workload, fused)) if world == 1 else None
     n_gu, ms_gu, _ = prof_u[capi.K_GSOP]
     n_iu, ms_iu, _ = prof_u[capi.K_INTERP]
     bpu_u = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
@@ -355,7 +355,7 @@ def main():
                   "bound": "hbm", "achieved": ach_u, "peak": peak, "unit": "GB/s", "frac": (ach_u / peak) if ach_u else None,
                   "bytes_per_update": bpu_u, "launches": n_gu, "ms_per_launch": ms_gu / max(1, n_gu),
                   "interp_kernel_ms_per_launch": ms_iu / max(1, n_iu),
-                  "traffic": {("cfg2"): 2.906e9}.get(args.workload) if world == 1 else None,
+                  "traffic": {("cfg2"): 2.895e9}.get(args.workload) if world == 1 else None,
                   "note": "same generations with GSGP_PIPELINE=unfused; not the timed `value` path"}
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
@@ -363,8 +363,9 @@ def main():
                 "launches": n_gs, "ms_total": ms_gs, "pipeline": "fused" if fused else "unfused",
                 "interp_kernel": {"launches": n_it, "ms_total": ms_it},
                 "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None},
-                "limiter": ("instruction issue (ncu: issue-active 69 %, fp64 pipe 40 %, DRAM 23 %): the fused kernel is "
-                            "not HBM-bound; see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
+                "limiter": ("issue slots 64 %, shared-memory wavefronts 59-64 %, fp64 pipe 43 %, DRAM 30 % (ncu, profiles/"
+                            "r01_gen_kernel_final_ncu_summary.csv): the fused kernel is balanced across the SM's pipes, not "
+                            "HBM-bound; see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
                 "gs_kernel_unfused": gs_unfused}
 
     cpu_baseline = None
