@@ -363,7 +363,7 @@ def main():
                 "launches": n_gs, "ms_total": ms_gs, "pipeline": "fused" if fused else "unfused",
                 "interp_kernel": {"launches": n_it, "ms_total": ms_it},
                 "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None},
-                "limiter": ("issue slots 64 %, shared-memory wavefronts 59-64 %, fp64 pipe 43 %, DRAM 30 % (ncu, profiles/"
+                "limiter": ("issue slots 63 %, shared-memory wavefronts 60-65 %, fp64 pipe 44 %, DRAM 31 % (ncu, profiles/"
                             "r01_gen_kernel_final_ncu_summary.csv): the fused kernel is balanced across the SM's pipes, not "
                             "HBM-bound; see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
                 "gs_kernel_unfused": gs_unfused}
