@@ -175,7 +175,8 @@ private:
 
 }  // namespace
 
-constexpr int kDrawSets = 3;
+constexpr int kDrawSets = 6;                                  // draws run kDrawSets-1 generations ahead ...
+constexpr int kDrawStreams = 3;                               // ... up to three of them at a time
 constexpr int kRunHistBlock = 64;
 
 struct gsgp_ctx {
@@ -223,8 +224,10 @@ struct gsgp_ctx {
         int32_t *cand = nullptr;                              // device mode: tournament candidates
     } ds[kDrawSets];
     int dcur = 0;                                             // set of the current / last generation
-    int32_t drawn[kDrawSets] = {-1, -1, -1};                  // generation whose draws sit in (or are on their way to) ds[i]
-    cudaStream_t stream2 = nullptr;                           // plan_draw_kernel
+    int32_t drawn[kDrawSets];                                 // generation whose draws sit in (or are on their way to) ds[i]
+    cudaStream_t stream2 = nullptr;                           // plan_draw_kernel (= draw_stream[0])
+    cudaStream_t draw_stream[kDrawStreams] = {};              // draws of consecutive generations overlap each other
+    bool draw_concurrent = false;                             // the draw kernel keeps its scratch in shared memory
     cudaEvent_t ev_draw[kDrawSets] = {}, ev_free[kDrawSets] = {};   // per draw set: filled / no longer read
     uint16_t *dpost_pool = nullptr;                           // device mode: postfix scratch of plan_draw_kernel
     uint32_t *dcompile_scratch = nullptr;                     // device mode: program-builder scratch
@@ -733,19 +736,22 @@ PlanArgs plan_args(gsgp_ctx *c, int32_t generation)
 int launch_draw(gsgp_ctx *c, int32_t generation)
 {
     const PlanArgs a = plan_args(c, generation);
-    CU(c, cudaStreamWaitEvent(c->stream2, c->ev_free[generation % kDrawSets], 0));
+    // the kernel is latency-bound (one thread builds an individual's trees), so at small populations it, not the
+    // generation kernels, sets the pace: draws of consecutive generations go to different streams and overlap
+    cudaStream_t st = c->draw_concurrent ? c->draw_stream[generation % kDrawStreams] : c->stream2;
+    CU(c, cudaStreamWaitEvent(st, c->ev_free[generation % kDrawSets], 0));
     {
-        ProfScope ps(c, GSGP_K_PLAN, 0.0, c->stream2);
+        ProfScope ps(c, GSGP_K_PLAN, 0.0, st);
         // working set of a thread: postfix + builder scratch, post_stride words each, in shared memory when a block of
         // >= 32 threads fits (depth <= 8); global scratch pools otherwise
         const size_t per_thread = 2 * (size_t)c->post_stride * sizeof(uint32_t);
         int nt = 0;
         for (int cand : {64, 32}) if (per_thread * cand <= (size_t)200 * 1024) { nt = cand; break; }
-        if (nt) plan_draw_kernel<true><<<(a.P + nt - 1) / nt, nt, per_thread * nt, c->stream2>>>(a);
-        else plan_draw_kernel<false><<<(a.P + 127) / 128, 128, 0, c->stream2>>>(a);
+        if (nt) plan_draw_kernel<true><<<(a.P + nt - 1) / nt, nt, per_thread * nt, st>>>(a);
+        else plan_draw_kernel<false><<<(a.P + 127) / 128, 128, 0, st>>>(a);
         CU(c, cudaGetLastError());
     }
-    CU(c, cudaEventRecord(c->ev_draw[generation % kDrawSets], c->stream2));
+    CU(c, cudaEventRecord(c->ev_draw[generation % kDrawSets], st));
     c->drawn[generation % kDrawSets] = generation;
     return 0;
 }
@@ -854,6 +860,7 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
 
     gsgp_ctx *c = new gsgp_ctx();
     c->cfg = *cfg;
+    std::fill(c->drawn, c->drawn + kDrawSets, -1);
     auto bail = [&](void) { g_create_error = c->err; gsgp_destroy(c); return 1; };
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fail(c, "%s failed: %s", #call, cudaGetErrorString(e__)); return bail(); } } while (0)
     CUC(cudaSetDevice(cfg->device));
@@ -965,7 +972,10 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         {   // the draw kernel is small and on the critical path of the NEXT generation: let its blocks go first
             int lo = 0, hi = 0;
             CUC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CUC(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+            for (int i = 0; i < kDrawStreams; ++i) CUC(cudaStreamCreateWithPriority(&c->draw_stream[i], cudaStreamNonBlocking, hi));
+            c->stream2 = c->draw_stream[0];
+            // concurrent draws only when each block keeps its scratch in shared memory (the global scratch pools are one copy)
+            c->draw_concurrent = 2 * (size_t)c->post_stride * sizeof(uint32_t) * 32 <= (size_t)200 * 1024;
         }
         for (int i = 0; i < kDrawSets; ++i) {
             CUC(cudaEventCreateWithFlags(&c->ev_draw[i], cudaEventDisableTiming));
@@ -1026,13 +1036,13 @@ void gsgp_destroy(gsgp_ctx *c)
     for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
     cudaFree(c->dsums2); cudaFree(c->dsums_all2); cudaFree(c->dab);
-    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) cudaStreamSynchronize(c->draw_stream[i]);
     for (int i = 0; i < kDrawSets; ++i) {
         cudaFree(c->ds[i].tree_pool); cudaFree(c->ds[i].prog_desc); cudaFree(c->ds[i].rec); cudaFree(c->ds[i].cand);
         if (c->ev_draw[i]) cudaEventDestroy(c->ev_draw[i]);
     }
     for (int i = 0; i < kDrawSets; ++i) if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) cudaStreamDestroy(c->draw_stream[i]);
     cudaFree(c->dplan); cudaFree(c->dprog_off);
     cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
     for (double *p : c->run_sem) cudaFree(p);
@@ -1367,14 +1377,15 @@ int gsgp_run_generations(gsgp_ctx *c, int32_t n)
     if (ensure_hist(c, c->generation + n)) return 1;
     for (int32_t i = 0; i < n; ++i) {
         const int32_t g = c->generation + 1;
-        // draws run two generations ahead on the second stream: those of g+2 start the moment gen_kernel(g) has
-        // released the draw set they overwrite, i.e. under the finalize kernels of g and the start of g+1, when
-        // SMs are free (a gen_kernel block fills an SM's shared memory; a draw block cannot squeeze in beside it)
-        if (c->drawn[g % kDrawSets] != g && launch_draw(c, g)) return 1;       // first calls / after gsgp_draw_plan
-        if (c->drawn[(g + 1) % kDrawSets] != g + 1 && launch_draw(c, g + 1)) return 1;
+        // draws run kDrawSets-1 generations ahead on high-priority streams: those of g+5 start the moment
+        // gen_kernel(g) has released the draw set they overwrite and run under the following generations whenever
+        // SMs are free (a gen_kernel block fills an SM's shared memory; a draw block cannot squeeze in beside it).
+        // Small populations are paced by the draw kernel's latency, hence several draws in flight.
+        for (int32_t d = 0; d < kDrawSets - 1; ++d)                            // first calls / after gsgp_draw_plan
+            if (c->drawn[(g + d) % kDrawSets] != g + d && launch_draw(c, g + d)) return 1;
         if (launch_select(c, g)) return 1;
-        if (run_generation_kernels(c, nullptr, max_sp)) return 1;              // records ev_free[g%3] behind the kernels that read the set
-        if (launch_draw(c, g + 2)) return 1;                                   // (its set was released by generation g-1)
+        if (run_generation_kernels(c, nullptr, max_sp)) return 1;              // records ev_free[g % sets] behind the kernels that read the set
+        if (launch_draw(c, g + kDrawSets - 1)) return 1;                       // (its set was released by generation g-1)
     }
     c->last_plan.clear();
     return 0;
@@ -1385,7 +1396,7 @@ int gsgp_sync(gsgp_ctx *c)
     if (!c) return fail(nullptr, "null context");
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->stream));
-    if (c->stream2) CU(c, cudaStreamSynchronize(c->stream2));
+    for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) CU(c, cudaStreamSynchronize(c->draw_stream[i]));
     return 0;
 }
 
@@ -1503,7 +1514,7 @@ int gsgp_draw_plan(gsgp_ctx *c, int32_t generation, gsgp_plan_entry *plan_out)
 {
     if (check_ready(c)) return 1;
     if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_draw_plan needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
-    CU(c, cudaStreamSynchronize(c->stream2));                          // pre-drawn generations are discarded
+    for (int i = 0; i < kDrawStreams; ++i) CU(c, cudaStreamSynchronize(c->draw_stream[i]));   // pre-drawn generations are discarded
     CU(c, cudaEventRecord(c->ev_free[generation % kDrawSets], c->stream));
     if (launch_draw(c, generation)) return 1;
     if (launch_select(c, generation)) return 1;
