@@ -175,8 +175,8 @@ private:
 
 }  // namespace
 
-constexpr int kDrawSets = 6;                                  // draws run kDrawSets-1 generations ahead ...
-constexpr int kDrawStreams = 3;                               // ... up to three of them at a time
+constexpr int kDrawSets = 8;                                  // draws run kDrawSets-1 generations ahead ...
+constexpr int kDrawStreams = 6;                               // ... up to six of them at a time
 constexpr int kRunHistBlock = 64;
 
 struct gsgp_ctx {
@@ -407,7 +407,7 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
     static const int32_t waves = getenv("GSGP_GEN_WAVES") ? std::max(1, atoi(getenv("GSGP_GEN_WAVES"))) : 8;
     const int32_t target = c->sm_count * waves;
     int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
-    groups = std::min(groups, std::max(1, (nk + 31) / 32));
+    groups = std::min(groups, std::max(1, (nk + kGenWarpsDefault - 1) / kGenWarpsDefault));   // >= one individual per warp
     int32_t ipg = (nk + groups - 1) / groups;
     while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
     groups = (nk + ipg - 1) / ipg;
@@ -1305,7 +1305,7 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
     int32_t max_sp = 0;
     if (!c->stage_pool) {
         // one process per GPU: leave cores for the other ranks' hosts (world_size processes share the box)
-        int nt = std::max(1, std::min(4, (int)std::thread::hardware_concurrency() / (2 * std::max(1, c->cfg.world_size))));
+        int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / (2 * std::max(1, c->cfg.world_size))));
         if (const char *e = getenv("GSGP_STAGE_THREADS")) nt = std::max(1, std::min(16, atoi(e)));
         c->stage_pool.reset(new StagePool(nt));
     }
@@ -1377,7 +1377,7 @@ int gsgp_run_generations(gsgp_ctx *c, int32_t n)
     if (ensure_hist(c, c->generation + n)) return 1;
     for (int32_t i = 0; i < n; ++i) {
         const int32_t g = c->generation + 1;
-        // draws run kDrawSets-1 generations ahead on high-priority streams: those of g+5 start the moment
+        // draws run kDrawSets-1 generations ahead on high-priority streams: those of g+7 start the moment
         // gen_kernel(g) has released the draw set they overwrite and run under the following generations whenever
         // SMs are free (a gen_kernel block fills an SM's shared memory; a draw block cannot squeeze in beside it).
         // Small populations are paced by the draw kernel's latency, hence several draws in flight.
