@@ -106,3 +106,14 @@ def test_malformed_trees_are_rejected():
     for bad in ([0, 3, 4, 4], [0, 1, 2], [0, 3, 4, 99, 4], [0, 0, 0, 4, 4], [9]):
         with pytest.raises(ValueError):
             compile_tree(bad, 6)
+
+
+def test_generated_division_ptx_is_current():
+    """go_gsgp_b200/csrc/interp_div.inc.h is generated: the checked-in text must be what tools/gen_interp_ptx.py renders."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_interp_ptx", os.path.join(root, "tools", "gen_interp_ptx.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert open(gen.TARGET).read() == gen.render(gen.DEFAULT_GROUP)
