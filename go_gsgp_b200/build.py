@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
         "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
         "-fmad=true",   # result-defining arithmetic uses __d*_rn intrinsics (never contracted)
-        "-o", LIB, *SOURCES, "-ldl",
+        "-o", LIB, *SOURCES, "-ldl", "-lz",
     ]
     if verbose:
         cmd.insert(1, "-Xptxas")

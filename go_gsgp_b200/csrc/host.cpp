@@ -4,7 +4,12 @@
 #include "program.hpp"
 #include "trees.hpp"
 
+#include <zlib.h>
+
 #include <charconv>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cmath>
 #include <thread>
 #include <cstdio>
@@ -482,6 +487,144 @@ int gsgph_format_semantic(const double *v, int64_t n, char *out, int64_t cap, in
     int64_t at = 0;
     for (auto &s : part) { memcpy(out + at, s.data(), s.size()); at += (int64_t)s.size(); }
     return 0;
+}
+
+// ---- output path: the reference's line writers, off the generation loop's critical path ---------
+// main_cpu.go writes, every generation, the best individual's fitness (:1495-1496) and its whole train / test semantic
+// (:1499-1500) as text through a writer that is a gzip stream when the path ends in ".gz" (:1227-1241; the defaults are
+// semantictrain.txt.gz / semantictest.txt.gz, :175-176).  At 1M+ cases that is tens of MB of text per generation:
+// formatting and deflate would dominate a fast loop.  gsgph_writer takes a COPY of the values and returns; a background
+// thread formats (multi-threaded shortest-digits %v) and compresses.  Compression is parallel: the text is cut into
+// blocks, each deflated as its own gzip member by a pool thread, members written in order -- a concatenation of gzip
+// members is a valid gzip file (Go's compress/gzip and Python's gzip read it as one stream).
+struct gsgph_writer {
+    FILE *f = nullptr;
+    bool gz = false;
+    int32_t n_threads = 4;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv_put, cv_get;
+    struct Job { std::vector<double> v; bool semantic; };
+    std::deque<Job> q;
+    size_t queued_bytes = 0;
+    bool closing = false, failed = false;
+    std::string pending;                               // text not yet written / compressed (small lines are batched)
+
+    static constexpr size_t kBlock = (size_t)4 << 20;  // text bytes per gzip member
+    static constexpr size_t kMaxQueued = (size_t)512 << 20;
+
+    static bool deflate_member(const char *src, size_t n, std::string &out)
+    {
+        z_stream zs{};
+        if (deflateInit2(&zs, Z_BEST_SPEED, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        out.resize(deflateBound(&zs, (uLong)n) + 64);
+        zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(src)); zs.avail_in = (uInt)n;
+        zs.next_out = reinterpret_cast<Bytef *>(&out[0]); zs.avail_out = (uInt)out.size();
+        const int rc = deflate(&zs, Z_FINISH);
+        out.resize(zs.total_out);
+        deflateEnd(&zs);
+        return rc == Z_STREAM_END;
+    }
+    // writes text[0, n): plain, or as ceil(n / kBlock) gzip members compressed in parallel
+    void emit(const char *text, size_t n)
+    {
+        if (!n || failed) return;
+        if (!gz) { if (fwrite(text, 1, n, f) != n) failed = true; return; }
+        const size_t nb = (n + kBlock - 1) / kBlock;
+        std::vector<std::string> out(nb);
+        std::vector<char> ok(nb, 1);
+        auto work = [&](size_t t, size_t stride) {
+            for (size_t b = t; b < nb; b += stride)
+                ok[b] = deflate_member(text + b * kBlock, std::min(kBlock, n - b * kBlock), out[b]);
+        };
+        const size_t nt = std::min<size_t>((size_t)std::max(1, n_threads), nb);
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; ++t) th.emplace_back(work, t, nt);
+        work(0, nt);
+        for (auto &x : th) x.join();
+        for (size_t b = 0; b < nb; ++b)
+            if (!ok[b] || fwrite(out[b].data(), 1, out[b].size(), f) != out[b].size()) { failed = true; return; }
+    }
+    void flush_pending(bool force)
+    {
+        if (pending.size() >= kBlock || (force && !pending.empty())) { emit(pending.data(), pending.size()); pending.clear(); }
+    }
+    void run()
+    {
+        std::string text;
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_get.wait(lk, [&] { return closing || !q.empty(); });
+                if (q.empty()) break;
+                job = std::move(q.front()); q.pop_front();
+                queued_bytes -= job.v.size() * sizeof(double);
+                cv_put.notify_all();
+            }
+            const int64_t n = (int64_t)job.v.size();
+            if (job.semantic) {
+                text.resize((size_t)n * 25 + 2);
+                int64_t len = 0;
+                gsgph_format_semantic(job.v.data(), n, &text[0], (int64_t)text.size() - 1, &len, n_threads);
+                text[(size_t)len] = '\n';
+                if ((size_t)len + 1 >= kBlock) {                         // a big line: its own members, in order
+                    flush_pending(true);
+                    emit(text.data(), (size_t)len + 1);
+                } else {
+                    pending.append(text.data(), (size_t)len + 1);
+                    flush_pending(false);
+                }
+            } else {
+                char buf[40];
+                for (double x : job.v) { const int k = format_go_v(x, buf); buf[k] = '\n'; pending.append(buf, (size_t)k + 1); }
+                flush_pending(false);
+            }
+        }
+        flush_pending(true);
+    }
+};
+
+gsgph_writer *gsgph_writer_open(const char *path, int32_t n_threads)
+{
+    if (!path) return nullptr;
+    FILE *f = fopen(path, "wb");                                         // os.Create, main_cpu.go:1229
+    if (!f) return nullptr;
+    gsgph_writer *w = new gsgph_writer();
+    w->f = f;
+    const size_t len = strlen(path);
+    w->gz = len >= 3 && strcmp(path + len - 3, ".gz") == 0;              // :1237
+    w->n_threads = n_threads > 0 ? n_threads : (int32_t)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    w->worker = std::thread([w] { w->run(); });
+    return w;
+}
+
+static int writer_put(gsgph_writer *w, const double *v, int64_t n, bool semantic)
+{
+    if (!w || (!v && n > 0) || n < 0) return 1;
+    gsgph_writer::Job job;
+    job.v.assign(v, v + n); job.semantic = semantic;
+    std::unique_lock<std::mutex> lk(w->mu);
+    if (w->closing) return 1;
+    w->cv_put.wait(lk, [&] { return w->queued_bytes < gsgph_writer::kMaxQueued; });   // back-pressure, not unbounded memory
+    w->queued_bytes += job.v.size() * sizeof(double);
+    w->q.push_back(std::move(job));
+    w->cv_get.notify_one();
+    return w->failed ? 2 : 0;
+}
+
+int gsgph_writer_semantic(gsgph_writer *w, const double *v, int64_t n) { return writer_put(w, v, n, true); }
+int gsgph_writer_float(gsgph_writer *w, double v) { return writer_put(w, &v, 1, false); }
+
+int gsgph_writer_close(gsgph_writer *w)
+{
+    if (!w) return 1;
+    { std::lock_guard<std::mutex> lk(w->mu); w->closing = true; w->cv_get.notify_all(); }
+    if (w->worker.joinable()) w->worker.join();
+    bool bad = w->failed;
+    if (fclose(w->f) != 0) bad = true;
+    delete w;
+    return bad ? 2 : 0;
 }
 
 }  // extern "C"

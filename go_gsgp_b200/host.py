@@ -42,6 +42,10 @@ HOST_SIGNATURES = {
     "gsgph_parse_floats": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64), C.c_int32]),
     "gsgph_compile_tree": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int32,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gsgph_writer_open": (C.c_void_p, [C.c_char_p, C.c_int32]),
+    "gsgph_writer_semantic": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int64]),
+    "gsgph_writer_float": (C.c_int, [C.c_void_p, C.c_double]),
+    "gsgph_writer_close": (C.c_int, [C.c_void_p]),
 }
 
 _bound = False
@@ -110,6 +114,40 @@ def compile_tree(tree, n_symbols):
     if rc:
         raise ValueError(f"malformed tree (gsgph_compile_tree rc={rc})")
     return out[0:2 * n.value:2].copy(), out[1:2 * n.value:2].copy(), need.value
+
+
+class LineWriter:
+    """The reference's per-generation output files (main_cpu.go:1227-1241,1494-1500): fitness lines and
+    best-individual semantic lines, gzip when the path ends in ".gz".  Writes are asynchronous: the values are
+    copied, a background thread formats and compresses."""
+
+    def __init__(self, path, n_threads=0):
+        self.L = _lib()
+        self.h = self.L.gsgph_writer_open(str(path).encode(), n_threads)
+        if not self.h:
+            raise OSError(f"cannot create {path}")
+
+    def write_semantic(self, sem):
+        sem = np.ascontiguousarray(sem, np.float64)
+        if self.L.gsgph_writer_semantic(self.h, capi.dptr(sem), len(sem)):
+            raise OSError("semantic line could not be queued")
+
+    def write_float(self, v):
+        if self.L.gsgph_writer_float(self.h, float(v)):
+            raise OSError("line could not be queued")
+
+    def close(self):
+        if self.h:
+            rc = self.L.gsgph_writer_close(self.h)
+            self.h = None
+            if rc:
+                raise OSError("output file could not be written completely")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 class HostDriver:

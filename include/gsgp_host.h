@@ -82,6 +82,16 @@ int gsgph_format_float(double v, char *buf, int32_t cap);
  * (:1499-1500).  Multi-threaded (n_threads <= 0: default); 25 bytes per value always suffice; non-zero if cap is short. */
 int gsgph_format_semantic(const double *v, int64_t n, char *out, int64_t cap, int64_t *len_out, int32_t n_threads);
 
+/* ---- asynchronous line writers for the per-generation outputs (main_cpu.go:1227-1241,1494-1500) ----------------
+ * A path ending in ".gz" is written as gzip (the reference's default for the semantic files, :175-176), anything
+ * else as plain text.  The calls copy their input and return; a background thread formats and compresses (parallel
+ * gzip members), so the generation loop never waits for text.  gsgph_writer_close drains and closes; 0 = all written. */
+typedef struct gsgph_writer gsgph_writer;
+gsgph_writer *gsgph_writer_open(const char *path, int32_t n_threads);          /* NULL if the file cannot be created */
+int gsgph_writer_semantic(gsgph_writer *w, const double *v, int64_t n);        /* fmt.Fprintln(file, Semantic) :1499-1500 */
+int gsgph_writer_float(gsgph_writer *w, double v);                            /* fmt.Fprintln(file, fit[best]) :1495-1496 */
+int gsgph_writer_close(gsgph_writer *w);
+
 #ifdef __cplusplus
 }
 #endif

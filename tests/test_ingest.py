@@ -85,3 +85,43 @@ def test_semantic_files(tmp_path):
     open(p, "a").write("abc\n")
     with pytest.raises(RuntimeError, match="Cannot parse"):
         read_semantic(p, n + 1)
+
+
+@pytest.mark.parametrize("suffix", [".txt", ".txt.gz"])
+def test_async_line_writer_matches_the_reference_format(tmp_path, suffix):
+    """gsgph_writer: best-individual semantic lines (Semantic.String() + newline, main_cpu.go:123-126,1499-1500) and
+    fitness lines (%v, :1495-1496), gzip when the path ends in .gz (:1236-1238).  Large lines are compressed as several
+    gzip members in parallel: the file must still read back as one stream, byte for byte what the synchronous
+    formatter produces."""
+    import gzip
+    from go_gsgp_b200 import host
+    rng = np.random.default_rng(9)
+    rows = [rng.normal(size=7), np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e21, 1e-7, 123456789.0, 5e-324]),
+            rng.normal(size=700_000) * 1e3,                        # ~13 MB of text: several 4 MB gzip members
+            np.array([]), rng.uniform(-1, 1, 33)]
+    path = tmp_path / ("semantictrain" + suffix)
+    with host.LineWriter(path, n_threads=4) as w:
+        for r in rows:
+            w.write_semantic(r)
+    want = "".join(host.format_semantic(r) + "\n" if len(r) else "\n" for r in rows)
+    opener = gzip.open if suffix.endswith(".gz") else open
+    with opener(path, "rt") as f:
+        got = f.read()
+    assert got == want
+    if suffix.endswith(".gz"):
+        raw = open(path, "rb").read()
+        assert raw.count(b"\x1f\x8b\x08") >= 4                      # parallel members
+        assert len(raw) < len(want) / 2
+    fpath = tmp_path / ("fitnesstrain" + suffix)
+    vals = [0.5, 1e-9, 12345.678, np.nan, np.inf, 3.0]
+    with host.LineWriter(fpath) as w:
+        for v in vals:
+            w.write_float(v)
+    with opener(fpath, "rt") as f:
+        assert f.read() == "".join(host.format_float(v) + "\n" for v in vals)
+
+
+def test_line_writer_reports_unwritable_paths(tmp_path):
+    from go_gsgp_b200 import host
+    with pytest.raises(OSError):
+        host.LineWriter(tmp_path / "no_such_dir" / "x.txt.gz")
