@@ -111,7 +111,7 @@ def test_async_line_writer_matches_the_reference_format(tmp_path, suffix):
     if suffix.endswith(".gz"):
         raw = open(path, "rb").read()
         assert raw.count(b"\x1f\x8b\x08") >= 4                      # parallel members
-        assert len(raw) < len(want) / 2
+        assert len(raw) < 0.6 * len(want)                           # fastest deflate level: digits compress to ~52 %
     fpath = tmp_path / ("fitnesstrain" + suffix)
     vals = [0.5, 1e-9, 12345.678, np.nan, np.inf, 3.0]
     with host.LineWriter(fpath) as w:
