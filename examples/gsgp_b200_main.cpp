@@ -65,18 +65,16 @@ int main(int argc, char **argv)
     int32_t index_best = 0;
     if (gsgp_fitness_all(ctx, fit.data(), fit_test.data(), &index_best)) die(ctx, "gsgp_fitness_all");
 
-    FILE *f_train = fopen((out_dir + "/fitnesstrain.txt").c_str(), "w"), *f_test = fopen((out_dir + "/fitnesstest.txt").c_str(), "w");
-    FILE *s_train = fopen((out_dir + "/semantic_train.txt").c_str(), "w"), *s_test = fopen((out_dir + "/semantic_test.txt").c_str(), "w");
+    // the reference's writers (:1227-1241), asynchronous: the rows are copied, text is produced off the loop
+    gsgph_writer *f_train = gsgph_writer_open((out_dir + "/fitnesstrain.txt").c_str(), 0), *f_test = gsgph_writer_open((out_dir + "/fitnesstest.txt").c_str(), 0);
+    gsgph_writer *s_train = gsgph_writer_open((out_dir + "/semantic_train.txt").c_str(), 0), *s_test = gsgph_writer_open((out_dir + "/semantic_test.txt").c_str(), 0);
     if (!f_train || !f_test || !s_train || !s_test) { fprintf(stderr, "panic: cannot create the output files\n"); return 2; }
-    std::vector<char> line((size_t)N * 25 + 64);
     auto write_best = [&] {                                                     // :1404-1411, :1494-1503
-        char buf[64];
-        gsgph_format_float(fit[(size_t)index_best], buf, sizeof buf); fprintf(f_train, "%s\n", buf);
-        gsgph_format_float(fit_test[(size_t)index_best], buf, sizeof buf); fprintf(f_test, "%s\n", buf);
+        gsgph_writer_float(f_train, fit[(size_t)index_best]);
+        gsgph_writer_float(f_test, fit_test[(size_t)index_best]);
         if (gsgp_get_semantic(ctx, index_best, sem.data())) die(ctx, "gsgp_get_semantic");
-        int64_t n = 0;
-        gsgph_format_semantic(sem.data(), nrow, line.data(), (int64_t)line.size(), &n, 0); fwrite(line.data(), 1, (size_t)n, s_train); fputc('\n', s_train);
-        gsgph_format_semantic(sem.data() + nrow, nrow_test, line.data(), (int64_t)line.size(), &n, 0); fwrite(line.data(), 1, (size_t)n, s_test); fputc('\n', s_test);
+        gsgph_writer_semantic(s_train, sem.data(), nrow);
+        gsgph_writer_semantic(s_test, sem.data() + nrow, nrow_test);
     };
     write_best();
 
@@ -88,7 +86,9 @@ int main(int argc, char **argv)
         if (gsgp_generation(ctx, plan.data(), trees.data(), tlen, fit.data(), fit_test.data(), &index_best)) die(ctx, "gsgp_generation");
         write_best();
     }
-    fclose(f_train); fclose(f_test); fclose(s_train); fclose(s_test);
+    if (gsgph_writer_close(f_train) | gsgph_writer_close(f_test) | gsgph_writer_close(s_train) | gsgph_writer_close(s_test)) {
+        fprintf(stderr, "panic: cannot write the output files\n"); return 2;
+    }
     gsgp_destroy(ctx);
     gsgph_rng_free(rng);
     gsgph_free(set);
