@@ -38,7 +38,10 @@ def main():
         o.create_T_F()
         e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE, rng_seed=5,
                    rng_mode=mode, device=local, rank=rank, world_size=world, nccl_id=fresh_nccl_id(),
-                   use_linear_scaling=(mode == capi.RNG_DEVICE_PHILOX))
+                   use_linear_scaling=(mode == capi.RNG_DEVICE_PHILOX),
+                   # the device-mode leg also runs on the single-buffer store (what config 5 uses at full size)
+                   flags=capi.FLAG_SINGLE_BUFFER_STORE if mode == capi.RNG_DEVICE_PHILOX else 0)
+        assert e.store_buffers == (1 if mode == capi.RNG_DEVICE_PHILOX else 2)
         want = os.environ.get("GSGP_EXCHANGE", "p2p")
         assert e.exchange == want, (e.exchange, want)       # the fused peer exchange is the default; NCCL on request
         e.set_dataset(X, y)
