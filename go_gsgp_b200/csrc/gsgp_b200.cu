@@ -141,6 +141,7 @@ public:
         for (auto &t : threads_) t.join();
     }
     std::vector<Job> &jobs() { return jobs_; }
+    void run_caller_only() { jobs_[0].run(); }       // small generations: waking the workers costs more than the work
     void run_all()                                   // job 0 on the caller, the others on the workers
     {
         { std::lock_guard<std::mutex> lk(m_); pending_ = (int)jobs_.size() - 1; ++epoch_; }
@@ -1326,12 +1327,17 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
         auto ts = now();
         const int32_t k0 = (int32_t)((int64_t)P * ch / n_chunks), k1 = (int32_t)((int64_t)P * (ch + 1) / n_chunks);
         const int32_t s0 = 2 * k0, ns = 2 * (k1 - k0);
+        const bool caller_only = ns <= 512 || nj == 1;                 // a few hundred trees compile in ~20 us
         for (int32_t j = 0; j < nj; ++j) {
             StagePool::Job &J = jobs[(size_t)j];
             J.pool = tree_pool; J.off = off.data(); J.len = len.data(); J.pool_len = pool_len; J.n_symbols = c->n_symbols;
             J.t0 = s0 + (int32_t)((int64_t)ns * j / nj); J.t1 = s0 + (int32_t)((int64_t)ns * (j + 1) / nj);
+            if (caller_only) { J.t0 = j == 0 ? s0 : s0 + ns; J.t1 = s0 + ns; }
         }
-        c->stage_pool->run_all();
+        if (caller_only) {
+            for (int32_t j = 1; j < nj; ++j) { jobs[(size_t)j].out.clear(); jobs[(size_t)j].bad_slot = -1; jobs[(size_t)j].stack_need = 0; }
+            c->stage_pool->run_caller_only();
+        } else c->stage_pool->run_all();
         const size_t base0 = base;
         for (const StagePool::Job &J : jobs) {
             if (J.bad_slot >= 0) return fail(c, "tree %d: %s", J.bad_slot, J.err);
