@@ -578,7 +578,10 @@ int launch_ls_pass(gsgp_ctx *c, int mode, const double *sem, const double *osum_
 
 // local partials -> (all-gather across ranks) -> fitness -> best-of-generation.  n_tiles: tiling of the partials
 // the generation kernels left (gsop: 2048-case tiles, gen_kernel: 256-case tiles)
-int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_tiles)
+int ensure_hist(gsgp_ctx *c, int32_t gen);
+
+// best_gen >= 0: best_individual of the new fitness rides in the same launch (history slot best_gen)
+int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_tiles, int32_t best_gen = -1)
 {
     const int P = c->cfg.population_size;
     const double *sums_all = nullptr;
@@ -601,8 +604,11 @@ int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_t
         FitnessArgs f{c->dplan, sums_all, c->dfit[old_buf], c->dfit_test[old_buf], c->dfit[new_buf],
                       c->dfit_test[new_buf], P, c->cfg.world_size, mode, c->cfg.error_measure,
                       c->cfg.nrow, c->cfg.nrow_test};
+        if (best_gen >= 0 && ensure_hist(c, best_gen)) return 1;
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
-        fitness_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(f);
+        if (best_gen >= 0)
+            fitness_best_kernel<<<1, 1024, 0, c->stream>>>(f, c->cfg.minimization_problem, c->dindex_best, c->dhist + best_gen);
+        else fitness_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(f);
         CU(c, cudaGetLastError());
     }
     return 0;
@@ -635,10 +641,10 @@ int ensure_run_history(gsgp_ctx *c, int32_t gen)
     return 0;
 }
 
-int launch_best(gsgp_ctx *c, int buf, int32_t gen)
+int launch_best(gsgp_ctx *c, int buf, int32_t gen, bool best_done = false)
 {
     if (ensure_hist(c, gen)) return 1;
-    {
+    if (!best_done) {
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
         best_kernel<<<1, 1024, 0, c->stream>>>(c->dfit[buf], c->dfit_test[buf], c->cfg.population_size,
                                                c->cfg.minimization_problem, c->dindex_best, c->dhist + gen);
@@ -662,10 +668,10 @@ int launch_best(gsgp_ctx *c, int buf, int32_t gen)
 int finish_generation(gsgp_ctx *c)
 {
     const int old_buf = c->cur, new_buf = c->cur ^ 1;
-    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, c->fused ? c->n_tiles_gen : c->n_tiles)) return 1;
+    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, c->fused ? c->n_tiles_gen : c->n_tiles, c->generation + 1)) return 1;
     c->cur = new_buf;                                                  // update_tables main_cpu.go:1191-1197
     c->generation++;
-    if (launch_best(c, c->cur, c->generation)) return 1;               // :1492
+    if (launch_best(c, c->cur, c->generation, true)) return 1;         // :1492 (best_individual rode in the fitness launch)
     c->fitness_valid = true;
     return 0;
 }
@@ -1267,8 +1273,8 @@ int gsgp_fitness_all(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_
         const int32_t nk = std::min(65535, P - k0);
         if (launch_gsop(c, GS_MODE_FITNESS_ONLY, k0, nk, 0, c->dsem[c->cur], c->dsem[c->cur], 8.0 * nk * n_cases)) return 1;
     }
-    if (launch_finalize(c, GS_MODE_FITNESS_ONLY, c->cur, c->cur, c->n_tiles)) return 1;
-    if (launch_best(c, c->cur, c->generation)) return 1;
+    if (launch_finalize(c, GS_MODE_FITNESS_ONLY, c->cur, c->cur, c->n_tiles, c->generation)) return 1;
+    if (launch_best(c, c->cur, c->generation, true)) return 1;
     c->fitness_valid = true;
     return read_fitness(c, fit, fit_test, index_best);
 }
