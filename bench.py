@@ -302,9 +302,17 @@ def main():
     # ---- e2e: host-replay mode through gsgp_generation() with host buffers -------------------------
     e, fit, best = setup(capi.RNG_HOST_REPLAY)
     h2d = d2h = 0
+    # the host's plan builder is pipelined (gsgph_planner_*, include/gsgp_host.h): the next generation's fitness-
+    # independent draws (operators, random trees, tournament candidates) are made on a worker thread while the
+    # device computes; winners are picked when the fitness arrives.  Same plans and RNG stream as build_plan.
+    planner = host.planner() if os.environ.get("GSGP_BENCH_PLANNER", "1") != "0" else None
     def replay_step(count=False):
         nonlocal fit, best, h2d, d2h
-        plan, pool = host.build_plan(fit, best)
+        if planner is not None:
+            plan, pool = planner.plan(fit, best)
+            planner.prefetch(best)
+        else:
+            plan, pool = host.build_plan(fit, best)
         fit, fit_test, best = e.generation(plan, pool)
         if count:
             # uploaded by the call: plan entries, accumulator programs (8 B per function node; a tree of i ints
@@ -324,6 +332,7 @@ def main():
     replay_step(count=True)
     ms_e2e = max_over_ranks((t1 - t0) * 1e3)
     e2e_value = updates_per_step * K / (ms_e2e * 1e-3)
+    planner_stats = planner.stats() if planner is not None else None
     e.close()
     clocks = sampler.stop()
 
@@ -389,7 +398,9 @@ def main():
                        "store": store, "exchange": exchange,
                        "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building"},
+                    "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building",
+                    "plan_builder": ("pipelined (gsgph_planner_*): elite-index guesses right/wrong = %d/%d" %
+                                     (planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)"},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }

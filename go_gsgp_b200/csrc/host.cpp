@@ -6,6 +6,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <charconv>
 #include <condition_variable>
 #include <deque>
@@ -19,16 +20,53 @@
 #include <vector>
 
 struct gsgph_rng {
-    uint64_t vec[607];
-    int tap, feed;
+    // Go's additive lagged Fibonacci source, s[n] = s[n-607] + s[n-273], kept as the last 607 outputs in time order
+    // and advanced 607 outputs at a time (dependence-free loops the compiler vectorises) instead of one modular
+    // step per draw: same stream, cheaper per draw.
+    uint64_t h[607];
+    // Raw outputs are read through a queue: [buf, end) holds what the source has produced, cur the next value the
+    // logical stream consumes.  While `recording` (gsgph_planner) consumed values stay in the queue, so a caller can
+    // note a position (tell) and go back to it (seek): the planner draws a generation before it knows that
+    // generation's elite index and, when the guess was wrong, consumes the same raw values again from the first
+    // individual whose draws change, in the reference's order.  The logical stream every caller sees is always the
+    // source's stream, whatever was re-read.
+    uint64_t *buf = nullptr, *cur = nullptr, *end = nullptr;
+    size_t cap = 0;
+    bool recording = false;
+    ~gsgph_rng() { free(buf); }
+    void seed_from_go_layout(const uint64_t *vec)               // rngSource's vec with tap = 0, feed = 607 - 273
+    {
+        for (int i = 0; i < 607; ++i) h[i] = vec[(333 - i + 607) % 607];
+        cur = end = buf;
+    }
+    __attribute__((noinline)) void more()                       // cur == end: the next 607 outputs
+    {
+        size_t size = recording ? (size_t)(end - buf) : 0;
+        if (size + 607 > cap) {
+            cap = std::max<size_t>(2 * cap, size + 4 * 607);
+            buf = static_cast<uint64_t *>(realloc(buf, cap * sizeof(uint64_t)));
+        }
+        for (int i = 0; i < 273; ++i) h[i] += h[i + 334];
+        for (int i = 273; i < 546; ++i) h[i] += h[i - 273];
+        for (int i = 546; i < 607; ++i) h[i] += h[i - 273];
+        memcpy(buf + size, h, sizeof(h));
+        cur = buf + size;
+        end = cur + 607;
+    }
     uint64_t next()
     {
-        if (--tap < 0) tap += 607;
-        if (--feed < 0) feed += 607;
-        const uint64_t x = vec[feed] + vec[tap];
-        vec[feed] = x;
-        return x;
+        if (__builtin_expect(cur == end, 0)) more();
+        return *cur++;
     }
+    void tape_begin()                                           // start recording; consumed values are dropped
+    {
+        const size_t left = (size_t)(end - cur);
+        if (left) memmove(buf, cur, left * sizeof(uint64_t));
+        cur = buf; end = buf + left;
+        recording = true;
+    }
+    size_t tell() const { return (size_t)(cur - buf); }
+    void seek(size_t pos) { cur = buf + pos; }
     int64_t int63() { return (int64_t)(next() & 0x7fffffffffffffffull); }
     int32_t int31() { return (int32_t)(int63() >> 32); }
     double float64()
@@ -51,7 +89,10 @@ struct gsgph_rng {
             c.mx = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)n);
             c.m = (((uint64_t)1 << 63) + (uint64_t)n - 1) / (uint64_t)n;
         }
-        int32_t v = int31();
+        return intn_tail(int31(), n, c);
+    }
+    int32_t intn_tail(int32_t v, int32_t n, const IntnCache &c)
+    {
         while (v > c.mx) v = int31();
         const uint32_t q = (uint32_t)(((unsigned __int128)(uint64_t)v * c.m) >> 63);
         return v - (int32_t)(q * (uint32_t)n);
@@ -95,6 +136,45 @@ struct TreeBuilder {
     const std::vector<int32_t> &build(int32_t max_depth, int kind) { t.clear(); node(0, max_depth, kind); return t; }
 };
 
+// create_grow_tree_arrays (:609-639) straight into `t` (room for 4 * 2^max_depth ints), iterative: pre-order with an
+// explicit stack of (slot to patch, depth), so the draws come in the reference's order (decision, then the symbol,
+// left subtree before right).  Random trees make "function or terminal?" a coin flip per node; with no constants
+// both outcomes take exactly one more draw, so the node is written without branching on the coin.
+inline int32_t grow_tree_array(gsgph_rng *r, const gsgph_params *p, int32_t *t)
+{
+    const int32_t max_depth = p->max_depth_creation, nvar = p->nvar;
+    const bool plain = p->num_constants == 0;
+    const int32_t mx = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)nvar);
+    const uint64_t m = (((uint64_t)1 << 63) + (uint64_t)nvar - 1) / (uint64_t)nvar;
+    int32_t patch[64];
+    int32_t dep[64];
+    int32_t n = 0, sp = 1;
+    patch[0] = -1; dep[0] = 0;
+    int32_t scratch = 0;
+    while (sp > 0) {
+        --sp;
+        const int32_t slot = patch[sp], d = dep[sp];
+        *(slot >= 0 ? t + slot : &scratch) = n;                              // the parent's child index (:617,:620 / :632,:635)
+        bool func;
+        if (d == 0 && !p->zero_depth) func = true;                          // :610
+        else if (d == max_depth) func = false;                              // :623
+        else func = r->intn(2) != 0;                                        // :626-638
+        if (plain) {                                                        // choose_function :458-460 / choose_terminal :466-468
+            int32_t v = r->int31();
+            if (__builtin_expect(!func && v > mx, 0)) { do v = r->int31(); while (v > mx); }   // Int31n's rejection (rare)
+            const int32_t q = (int32_t)(((unsigned __int128)(uint64_t)v * m) >> 63);         // v / nvar (see IntnCache)
+            t[n] = func ? (v & (kFunc - 1)) : kFunc + (v - q * nvar);
+        } else if (func) t[n] = r->intn(kFunc);
+        else if (r->float64() < 0.7) t[n] = kFunc + r->intn(nvar);          // :469-473
+        else t[n] = kFunc + nvar + r->intn(p->num_constants);
+        patch[sp] = n + 2; dep[sp] = d + 1;                                 // right child: popped after the whole left subtree
+        patch[sp + 1] = n + 1; dep[sp + 1] = d + 1;
+        sp += func ? 2 : 0;
+        n += func ? 3 : 1;
+    }
+    return n;
+}
+
 inline bool better(const gsgph_params *p, double a, double b) { return p->minimization_problem ? a < b : a > b; }
 
 int32_t tournament(gsgph_rng *r, const gsgph_params *p, const double *fit)      // :830-840
@@ -107,6 +187,56 @@ int32_t tournament(gsgph_rng *r, const gsgph_params *p, const double *fit)      
     return best;
 }
 
+
+// individuals [k_from, P) of one generation's decisions (:1447-1470), drawn in the reference's order.
+// Returns true when the tree pool is too small.
+bool build_range(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t index_best, int32_t k_from,
+                 gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t &used_io)
+{
+    TreeBuilder tb{r, p, {}};
+    bool overflow = false;
+    int32_t used = used_io;
+    const int64_t tree_max = p->max_depth_creation < 20 ? ((int64_t)4 << p->max_depth_creation) : INT32_MAX;
+    auto new_tree = [&](int32_t &off, int32_t &len) {
+        if (used + tree_max <= cap) {                                          // room for any tree: built in place
+            off = used; len = grow_tree_array(r, p, pool + used); used += len;
+            return;
+        }
+        const std::vector<int32_t> &t = tb.build(p->max_depth_creation, 0);
+        if (used + (int64_t)t.size() > cap) { overflow = true; off = -1; len = 0; return; }
+        memcpy(pool + used, t.data(), t.size() * sizeof(int32_t));
+        off = used; len = (int32_t)t.size(); used += len;
+    };
+    for (int32_t k = k_from; k < p->population_size; ++k) {
+        gsgp_plan_entry &e = plan[k];
+        e.op = GSGP_OP_REPR; e.elite = (k == index_best); e.p1 = -1; e.p2 = -1;
+        e.tree0_off = -1; e.tree0_len = 0; e.tree1_off = -1; e.tree1_len = 0; e.ms = 0.0;
+        const double rand_num = r->float64();                                   // :1451
+        if (rand_num < p->p_crossover) {                                        // :1453
+            e.op = GSGP_OP_XO;
+            if (k != index_best) {
+                new_tree(e.tree0_off, e.tree0_len);                             // :879
+                e.p1 = tournament(r, p, fit);                                   // :881
+                e.p2 = tournament(r, p, fit);                                   // :882
+            } else e.p1 = k;
+        } else if (rand_num < p->p_crossover + p->p_mutation) {                 // :1459
+            e.op = GSGP_OP_MUT;
+            e.p1 = (k != index_best) ? tournament(r, p, fit) : k;               // :847-850
+            if (k != index_best) {
+                e.ms = r->float64();                                            // :919
+                new_tree(e.tree0_off, e.tree0_len);                             // :921
+                new_tree(e.tree1_off, e.tree1_len);                             // :922
+            }
+        } else {
+            e.op = GSGP_OP_REPR;                                                // :1467-1469
+            e.p1 = (k != index_best) ? tournament(r, p, fit) : k;
+        }
+        if (overflow) break;
+    }
+    used_io = used;
+    return overflow;
+}
+
 }  // namespace
 
 extern "C" {
@@ -114,14 +244,15 @@ extern "C" {
 gsgph_rng *gsgph_rng_new(int64_t seed)
 {
     gsgph_rng *r = new gsgph_rng();
+    uint64_t vec[607];
     uint64_t x = (uint64_t)seed;
     for (int i = 0; i < 607; ++i) {
         uint64_t z = (x += 0x9E3779B97F4A7C15ull);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        r->vec[i] = z ^ (z >> 31);
+        vec[i] = z ^ (z >> 31);
     }
-    r->tap = 0; r->feed = 607 - 273;
+    r->seed_from_go_layout(vec);
     return r;
 }
 void gsgph_rng_free(gsgph_rng *r) { delete r; }
@@ -172,41 +303,8 @@ int gsgph_initialize_population(gsgph_rng *r, const gsgph_params *p, int32_t n_s
 int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t index_best,
                      gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t *pool_len)
 {
-    TreeBuilder tb{r, p, {}};
     int32_t used = 0;
-    bool overflow = false;
-    auto new_tree = [&](int32_t &off, int32_t &len) {
-        const std::vector<int32_t> &t = tb.build(p->max_depth_creation, 0);
-        if (used + (int64_t)t.size() > cap) { overflow = true; off = -1; len = 0; return; }
-        memcpy(pool + used, t.data(), t.size() * sizeof(int32_t));
-        off = used; len = (int32_t)t.size(); used += len;
-    };
-    for (int32_t k = 0; k < p->population_size; ++k) {
-        gsgp_plan_entry &e = plan[k];
-        e.op = GSGP_OP_REPR; e.elite = (k == index_best); e.p1 = -1; e.p2 = -1;
-        e.tree0_off = -1; e.tree0_len = 0; e.tree1_off = -1; e.tree1_len = 0; e.ms = 0.0;
-        const double rand_num = r->float64();                                   // :1451
-        if (rand_num < p->p_crossover) {                                        // :1453
-            e.op = GSGP_OP_XO;
-            if (k != index_best) {
-                new_tree(e.tree0_off, e.tree0_len);                             // :879
-                e.p1 = tournament(r, p, fit);                                   // :881
-                e.p2 = tournament(r, p, fit);                                   // :882
-            } else e.p1 = k;
-        } else if (rand_num < p->p_crossover + p->p_mutation) {                 // :1459
-            e.op = GSGP_OP_MUT;
-            e.p1 = (k != index_best) ? tournament(r, p, fit) : k;               // :847-850
-            if (k != index_best) {
-                e.ms = r->float64();                                            // :919
-                new_tree(e.tree0_off, e.tree0_len);                             // :921
-                new_tree(e.tree1_off, e.tree1_len);                             // :922
-            }
-        } else {
-            e.op = GSGP_OP_REPR;                                                // :1467-1469
-            e.p1 = (k != index_best) ? tournament(r, p, fit) : k;
-        }
-        if (overflow) break;
-    }
+    const bool overflow = build_range(r, p, fit, index_best, 0, plan, pool, cap, used);
     if (pool_len) *pool_len = used;
     return overflow ? 1 : 0;
 }
@@ -248,6 +346,226 @@ int32_t gsgph_best_individual(const gsgph_params *p, const double *fit)
     int32_t best = 0;
     for (int32_t i = 1; i < p->population_size; ++i) if (better(p, fit[i], fit[best])) best = i;
     return best;
+}
+
+// ---- pipelined planner ------------------------------------------------------------------------------------------
+// gsgph_build_plan is serial with the device: generation g+1's plan needs generation g's fitness.  But only the
+// tournament WINNERS need fitness values; the operator draw, the random trees, the mutation step and the tournament
+// CANDIDATES need nothing but the RNG -- and the elite index (the elite slot skips its draws, :847,:877,:918).  The
+// elite keeps its index unless a strictly better child appears, so the planner draws generation g+1 on a worker
+// thread while the device computes generation g, guessing the elite, and finishes the plan when the fitness arrives:
+// winners among the recorded candidates, and -- when the guess was wrong -- individuals from the first differing slot
+// on redrawn from the recorded raw RNG values (gsgph_rng's tape), so the plan and the RNG stream are exactly those
+// gsgph_build_plan would have produced.
+struct gsgph_planner {
+    gsgph_rng *r;
+    gsgph_params p;
+    struct Rec { size_t tape_pos; int32_t pool_used; int32_t ncand; };      // per individual: where its draws start
+    std::vector<Rec> rec;
+    std::vector<int32_t> cand;                                              // [P][2][tournament_size]
+    std::vector<gsgp_plan_entry> plan[2];
+    std::vector<int32_t> pool[2];                                           // grown on demand up to pool_max
+    size_t pool_max = 0;
+    int cur = 0;                                                            // buffers the last gsgph_planner_plan returned
+    int32_t guess = -1, used = 0;
+    bool pending = false, overflow = false;
+    int64_t hits = 0, misses = 0, redrawn = 0;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    enum { IDLE, REQUESTED, QUIT } state = IDLE;
+
+    void draw_candidates(int32_t *c)
+    {
+        for (int i = 0; i < p.tournament_size; ++i) c[i] = r->intn(p.population_size);     // :831,:834
+    }
+    int32_t winner(const int32_t *c, const double *fit) const                              // :830-840
+    {
+        int32_t best = c[0];
+        for (int i = 1; i < p.tournament_size; ++i)
+            if (better(&p, fit[c[i]], fit[best])) best = c[i];
+        return best;
+    }
+    bool grow_pool(int b)                                                   // false: already at the worst-case size
+    {
+        if (pool[b].size() >= pool_max) return false;
+        pool[b].resize(std::min(pool_max, pool[b].size() * 2));
+        return true;
+    }
+    // everything of one generation that does not need fitness values, into the buffers `cur ^ 1`
+    void draw()
+    {
+        r->tape_begin();
+        for (;;) {
+            draw_once();
+            if (!overflow || !grow_pool(cur ^ 1)) return;
+            r->seek(0);                                                    // same raw values, larger pool
+        }
+    }
+    void draw_once()
+    {
+        gsgp_plan_entry *pl = plan[cur ^ 1].data();
+        int32_t *po = pool[cur ^ 1].data();
+        const int32_t cap = (int32_t)pool[cur ^ 1].size(), ts = p.tournament_size;
+        TreeBuilder tb{r, &p, {}};
+        used = 0; overflow = false;
+        const int64_t tree_max = p.max_depth_creation < 20 ? ((int64_t)4 << p.max_depth_creation) : INT32_MAX;
+        auto new_tree = [&](int32_t &off, int32_t &len) {
+            if (used + tree_max <= cap) {
+                off = used; len = grow_tree_array(r, &p, po + used); used += len;
+                return;
+            }
+            const std::vector<int32_t> &t = tb.build(p.max_depth_creation, 0);
+            if (used + (int64_t)t.size() > cap) { overflow = true; off = -1; len = 0; return; }
+            memcpy(po + used, t.data(), t.size() * sizeof(int32_t));
+            off = used; len = (int32_t)t.size(); used += len;
+        };
+        for (int32_t k = 0; k < p.population_size && !overflow; ++k) {
+            gsgp_plan_entry &e = pl[k];
+            int32_t *c = cand.data() + (size_t)k * 2 * ts;
+            rec[(size_t)k] = {r->tell(), used, 0};
+            e.op = GSGP_OP_REPR; e.elite = (k == guess); e.p1 = k; e.p2 = -1;
+            e.tree0_off = -1; e.tree0_len = 0; e.tree1_off = -1; e.tree1_len = 0; e.ms = 0.0;
+            const double rand_num = r->float64();                                   // :1451
+            if (rand_num < p.p_crossover) {                                         // :1453
+                e.op = GSGP_OP_XO;
+                if (e.elite) continue;
+                new_tree(e.tree0_off, e.tree0_len);                                 // :879
+                draw_candidates(c); draw_candidates(c + ts);                        // :881-882
+                rec[(size_t)k].ncand = 2;
+            } else if (rand_num < p.p_crossover + p.p_mutation) {                   // :1459
+                e.op = GSGP_OP_MUT;
+                if (e.elite) continue;
+                draw_candidates(c);                                                 // :847-850
+                rec[(size_t)k].ncand = 1;
+                e.ms = r->float64();                                                // :919
+                new_tree(e.tree0_off, e.tree0_len);                                 // :921
+                new_tree(e.tree1_off, e.tree1_len);                                 // :922
+            } else {
+                if (e.elite) continue;                                              // :1467-1469
+                draw_candidates(c);
+                rec[(size_t)k].ncand = 1;
+            }
+        }
+    }
+    void loop()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return state != IDLE; });
+            if (state == QUIT) return;
+            lk.unlock();
+            draw();
+            lk.lock();
+            state = IDLE;
+            cv.notify_all();
+        }
+    }
+};
+
+gsgph_planner *gsgph_planner_new(gsgph_rng *r, const gsgph_params *p)
+{
+    if (!r || !p || p->population_size <= 0 || p->tournament_size <= 0 || p->max_depth_creation < 0 || p->max_depth_creation > 20) return nullptr;
+    gsgph_planner *pl = new gsgph_planner();
+    pl->r = r; pl->p = *p;
+    const size_t P = (size_t)p->population_size;
+    const size_t tree_cap = ((size_t)4 << p->max_depth_creation);           // a depth-d tree has at most 4*2^d - 3 ints
+    pl->rec.resize(P);
+    pl->cand.resize(P * 2 * (size_t)p->tournament_size);
+    pl->pool_max = std::min<size_t>(2 * P * tree_cap, (size_t)INT32_MAX);
+    for (int b = 0; b < 2; ++b) { pl->plan[b].resize(P); pl->pool[b].resize(std::min<size_t>(pl->pool_max, 64 * P + 1024)); }
+    pl->worker = std::thread([pl] { pl->loop(); });
+    return pl;
+}
+
+static void planner_wait(gsgph_planner *pl)
+{
+    std::unique_lock<std::mutex> lk(pl->mu);
+    pl->cv.wait(lk, [&] { return pl->state == gsgph_planner::IDLE; });
+}
+
+void gsgph_planner_free(gsgph_planner *pl)
+{
+    if (!pl) return;
+    planner_wait(pl);
+    {
+        std::lock_guard<std::mutex> lk(pl->mu);
+        pl->state = gsgph_planner::QUIT;
+    }
+    pl->cv.notify_all();
+    pl->worker.join();
+    // a prefetched generation that was never asked for: its draws go back to the stream
+    if (pl->pending) pl->r->seek(pl->rec[0].tape_pos);
+    pl->r->recording = false;
+    delete pl;
+}
+
+int gsgph_planner_prefetch(gsgph_planner *pl, int32_t index_best_guess)
+{
+    if (!pl) return 1;
+    planner_wait(pl);
+    if (pl->pending) return 2;                                              // one generation ahead, not more
+    pl->guess = index_best_guess;
+    pl->pending = true;
+    {
+        std::lock_guard<std::mutex> lk(pl->mu);
+        pl->state = gsgph_planner::REQUESTED;
+    }
+    pl->cv.notify_all();
+    return 0;
+}
+
+int gsgph_planner_plan(gsgph_planner *pl, const double *fit, int32_t index_best, const gsgp_plan_entry **plan_out,
+                       const int32_t **pool_out, int32_t *pool_len)
+{
+    if (!pl || !fit) return 1;
+    planner_wait(pl);
+    const int32_t P = pl->p.population_size, ts = pl->p.tournament_size;
+    const int nxt = pl->cur ^ 1;
+    gsgp_plan_entry *plan = pl->plan[nxt].data();
+    bool overflow = false;
+    // individuals [m, P) drawn serially with the fitness at hand, from the raw values at tape position pos on
+    auto serial_from = [&](int32_t m, size_t pos, int32_t used0) {
+        for (;;) {
+            pl->r->seek(pos);
+            int32_t used = used0;
+            overflow = build_range(pl->r, &pl->p, fit, index_best, m, plan, pl->pool[nxt].data(), (int32_t)pl->pool[nxt].size(), used);
+            pl->used = used;
+            if (!overflow || !pl->grow_pool(nxt)) return;
+        }
+    };
+    if (!pl->pending) {                                                     // nothing prefetched: the plain serial build
+        pl->r->tape_begin();
+        serial_from(0, 0, 0);
+    } else {
+        pl->pending = false;
+        overflow = pl->overflow;                                            // only at the worst-case pool size
+        const int32_t m = overflow ? P : (index_best == pl->guess ? P : std::max(0, std::min(index_best, pl->guess)));
+        for (int32_t k = 0; k < m; ++k) {                                   // winners among the drawn candidates
+            const gsgph_planner::Rec &rc = pl->rec[(size_t)k];
+            const int32_t *c = pl->cand.data() + (size_t)k * 2 * ts;
+            if (rc.ncand >= 1) plan[k].p1 = pl->winner(c, fit);
+            if (rc.ncand == 2) plan[k].p2 = pl->winner(c + ts, fit);
+        }
+        if (m < P) {                                                        // wrong guess: slots m.. consume the same raw values again
+            serial_from(m, pl->rec[(size_t)m].tape_pos, pl->rec[(size_t)m].pool_used);
+            ++pl->misses; pl->redrawn += P - m;
+        } else if (!overflow) ++pl->hits;
+    }
+    const int32_t *pool = pl->pool[nxt].data();
+    pl->r->recording = false;
+    pl->cur = nxt;
+    if (plan_out) *plan_out = plan;
+    if (pool_out) *pool_out = pool;
+    if (pool_len) *pool_len = pl->used;
+    return overflow ? 3 : 0;
+}
+
+void gsgph_planner_stats(const gsgph_planner *pl, int64_t *hits, int64_t *misses, int64_t *redrawn)
+{
+    if (hits) *hits = pl ? pl->hits : 0;
+    if (misses) *misses = pl ? pl->misses : 0;
+    if (redrawn) *redrawn = pl ? pl->redrawn : 0;
 }
 
 // strconv.FormatFloat(v, 'g', -1, 64) as fmt's %v prints it: shortest round-trip digits, exponent

@@ -31,6 +31,12 @@ HOST_SIGNATURES = {
     "gsgph_build_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.POINTER(C.c_double), C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_best_individual": (C.c_int32, [C.POINTER(HostParams), C.POINTER(C.c_double)]),
+    "gsgph_planner_new": (C.c_void_p, [C.c_void_p, C.POINTER(HostParams)]),
+    "gsgph_planner_free": (None, [C.c_void_p]),
+    "gsgph_planner_prefetch": (C.c_int, [C.c_void_p, C.c_int32]),
+    "gsgph_planner_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
+    "gsgph_planner_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gsgph_build_effects_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.c_void_p,
                                            C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "gsgph_format_float": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
@@ -150,6 +156,51 @@ class LineWriter:
         self.close()
 
 
+class Planner:
+    """gsgph_planner_*: build_plan's result with the fitness-independent draws made on a worker thread while the
+    device computes the previous generation.  plan(fit, best) -> (plan, pool) views valid until the next plan();
+    prefetch(best) starts the following generation's draws."""
+
+    def __init__(self, driver: "HostDriver"):
+        self.L = driver.L
+        self.driver = driver                                     # keeps the rng alive
+        self.h = self.L.gsgph_planner_new(driver.rng, C.byref(driver.p))
+        if not self.h:
+            raise ValueError("gsgph_planner_new: bad parameters")
+        self.P = driver.P
+
+    def plan(self, fit, index_best):
+        fit = np.ascontiguousarray(fit, np.float64)
+        plan_p, pool_p, n = C.c_void_p(), C.POINTER(C.c_int32)(), C.c_int32()
+        rc = self.L.gsgph_planner_plan(self.h, capi.dptr(fit), int(index_best), C.byref(plan_p), C.byref(pool_p), C.byref(n))
+        if rc:
+            raise RuntimeError(f"gsgph_planner_plan failed ({rc})")
+        plan = np.frombuffer((C.c_char * (PLAN_DTYPE.itemsize * self.P)).from_address(plan_p.value), dtype=PLAN_DTYPE)
+        pool = np.ctypeslib.as_array(pool_p, shape=(max(n.value, 1),))
+        return plan, pool
+
+    def prefetch(self, index_best_guess):
+        rc = self.L.gsgph_planner_prefetch(self.h, int(index_best_guess))
+        if rc:
+            raise RuntimeError(f"gsgph_planner_prefetch failed ({rc})")
+
+    def stats(self):
+        h, m, r = C.c_int64(), C.c_int64(), C.c_int64()
+        self.L.gsgph_planner_stats(self.h, C.byref(h), C.byref(m), C.byref(r))
+        return {"hits": h.value, "misses": m.value, "redrawn_individuals": r.value}
+
+    def close(self):
+        if self.h:
+            self.L.gsgph_planner_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostDriver:
     """The RNG-order-defining half of main_cpu.go's main(): seeds the RNG, draws the constants,
     builds the initial population and, each generation, the plan the device applies."""
@@ -169,6 +220,8 @@ class HostDriver:
         self._pool = np.zeros(2 * self.P * self._tree_cap, np.int32)
 
     def close(self):
+        for pl in getattr(self, "_planners", []):               # a planner's worker draws from this rng
+            pl.close()
         if self.rng:
             self.L.gsgph_rng_free(self.rng)
             self.rng = None
@@ -204,6 +257,11 @@ class HostDriver:
         if rc:
             raise RuntimeError("gsgph_build_plan: tree pool overflow")
         return self._plan, self._pool[: max(used.value, 1)]
+
+    def planner(self) -> Planner:
+        pl = Planner(self)
+        self.__dict__.setdefault("_planners", []).append(pl)
+        return pl
 
     def build_effects_plan(self, test_crossover: bool):
         """operators_effects.go's single step (XO-only with uniform parents, or self-copy + mutation) as a plan."""

@@ -50,6 +50,28 @@ int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int
 
 int32_t gsgph_best_individual(const gsgph_params *p, const double *fit);     /* :1180-1188 */
 
+/* ---- pipelined planner: gsgph_build_plan's result, with the fitness-independent draws made while the device works
+ * Generation g+1's plan needs generation g's fitness only for the tournament WINNERS (:835) and for the elite index
+ * (the elite slot skips its draws, :847,:877,:918).  gsgph_planner_prefetch starts a worker thread drawing the next
+ * generation -- operators, random trees, mutation steps, tournament CANDIDATES -- under a guess of its elite index
+ * (the index just used: the elite keeps its slot unless a strictly better child appears); gsgph_planner_plan, called
+ * when the fitness is there, picks the winners and, if the guess was wrong, redraws the individuals from the first
+ * affected slot on from the recorded raw RNG values.  Plans, tree pools and the RNG stream are exactly those of
+ * gsgph_build_plan called once per generation (tests/test_host_driver.py).  While a planner exists the rng belongs to
+ * it between prefetch and plan.  Typical loop:
+ *     gsgph_planner_plan(pl, fit, best, &plan, &pool, &len);      // generation g+1 (first call: drawn on the spot)
+ *     gsgph_planner_prefetch(pl, best);                           // g+2's draws start now ...
+ *     gsgp_generation(ctx, plan, pool, len, fit, fit_test, &best);// ... and run under this call
+ * A Go host gets the same effect with a goroutine and a rand.Source wrapper that records Int63. */
+typedef struct gsgph_planner gsgph_planner;
+gsgph_planner *gsgph_planner_new(gsgph_rng *r, const gsgph_params *p);        /* NULL on bad parameters */
+void gsgph_planner_free(gsgph_planner *pl);                 /* draws of an unused prefetch go back to the stream */
+int gsgph_planner_prefetch(gsgph_planner *pl, int32_t index_best_guess);      /* 2: a prefetch is already pending */
+/* plan/pool stay valid until the next gsgph_planner_plan call returns; 3: tree pool exhausted */
+int gsgph_planner_plan(gsgph_planner *pl, const double *fit, int32_t index_best, const gsgp_plan_entry **plan,
+                       const int32_t **pool, int32_t *pool_len);
+void gsgph_planner_stats(const gsgph_planner *pl, int64_t *hits, int64_t *misses, int64_t *redrawn_individuals);
+
 /* the one-step experiment of operators_effects.go:1246-1256 as a plan for gsgp_generation: test_crossover != 0 ->
  * every individual is a crossover of two UNIFORMLY drawn parents (random_selection :783-786, :800-806); else every
  * individual is copied onto itself and mutated (:790-797, :836-842).  index_best is never assigned in that program,

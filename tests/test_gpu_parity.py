@@ -863,3 +863,37 @@ def test_randomized_configurations_lockstep(case):
     if not diverged:
         assert_close(e.get_semantics(), o.semantics(), TOL, f"semantics {kw}")
     e.close(); o.close()
+
+
+@pytest.mark.gpu
+def test_pipelined_planner_drives_the_same_run_as_build_plan():
+    """host replay with the pipelined plan builder (gsgph_planner_*: draws made on a worker thread while the device
+    computes, winners and wrong elite guesses settled when the fitness arrives) = host replay with gsgph_build_plan:
+    identical plans, fitness and best index, generation after generation."""
+    from go_gsgp_b200 import Engine, capi
+    from go_gsgp_b200.host import HostDriver
+    X, y, nrow = synth_dataset(3, 1250, 5, nrow=1000)
+    runs = []
+    for pipelined in (False, True):
+        h = HostDriver(population_size=100, nvar=5, seed=4)
+        sym, trees = h.create_T_F(), h.initialize_population(0)
+        e = Engine(population_size=100, nvar=5, nrow=nrow, nrow_test=len(y) - nrow, error_measure=capi.RMSE)
+        e.set_dataset(X, y); e.set_constants(sym); e.eval_initial(0, trees)
+        fit, fit_test, best = e.fitness_all()
+        pl = h.planner() if pipelined else None
+        hist = []
+        for g in range(40):
+            if pl is None:
+                plan, pool = h.build_plan(fit, best)
+            else:
+                plan, pool = pl.plan(fit, best)
+                pl.prefetch(best)
+            hist.append((plan.tobytes(), pool.tobytes()))
+            fit, fit_test, best = e.generation(plan, pool)
+            hist.append((fit.tobytes(), fit_test.tobytes(), best))
+        if pl is not None:
+            st = pl.stats()
+            assert st["hits"] + st["misses"] == 39
+        e.close(); h.close()
+        runs.append(hist)
+    assert runs[0] == runs[1]

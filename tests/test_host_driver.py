@@ -77,3 +77,69 @@ def test_format_semantic_line():
     back = np.array([float(p.replace("+Inf", "inf").replace("-Inf", "-inf")) for p in parts])
     assert np.array_equal(back[:-1], sem[:-1]) and np.isnan(back[-1])        # shortest digits round-trip exactly
     assert format_semantic(np.array([3.14, 2.71, 1.41])) == "3.14,2.71,1.41"  # the example in the reference's comment
+
+
+def _fitness_walk(P, gens, seed, p_change):
+    """a fitness history in which the best index moves in a fraction p_change of the generations (ties, NaN included)"""
+    rng = np.random.default_rng(seed)
+    best = int(rng.integers(P))
+    out = []
+    for g in range(gens):
+        fit = rng.uniform(1.0, 2.0, P)
+        fit[rng.integers(P, size=max(1, P // 10))] = 1.5        # ties among the candidates
+        if g % 7 == 3:
+            fit[rng.integers(P)] = np.nan                       # NaN never wins a tournament
+        if rng.uniform() < p_change:
+            best = int(rng.integers(P))
+        fit[best] = 0.5
+        out.append((fit, best))
+    return out
+
+
+@pytest.mark.parametrize("kw,p_change", [
+    (dict(population_size=100), 0.5),
+    (dict(population_size=100), 0.0),
+    (dict(population_size=257, num_constants=5, max_depth_creation=8, tournament_size=3, zero_depth=True), 0.3),
+    (dict(population_size=40, p_crossover=0.1, p_mutation=0.8, minimization_problem=False, tournament_size=1), 1.0),
+    (dict(population_size=3, max_depth_creation=10), 0.6),     # tree pool grows on demand
+])
+def test_pipelined_planner_equals_build_plan(kw, p_change):
+    """gsgph_planner_* (draws made ahead under a guessed elite index, winners and wrong guesses settled when the
+    fitness arrives) against gsgph_build_plan on a second RNG with the same seed: identical plans, pools and RNG
+    streams, generation after generation."""
+    from go_gsgp_b200.host import HostDriver
+    minimize = kw.get("minimization_problem", True)
+    a, b = HostDriver(nvar=7, seed=5, **kw), HostDriver(nvar=7, seed=5, **kw)
+    pl = b.planner()
+    P = kw["population_size"]
+    for g, (fit, best) in enumerate(_fitness_walk(P, 60, 11, p_change)):
+        if not minimize:
+            fit = -fit
+        plan_a, pool_a = a.build_plan(fit, best)
+        plan_b, pool_b = pl.plan(fit, best)
+        assert plan_a.tobytes() == plan_b.tobytes(), f"generation {g}"
+        np.testing.assert_array_equal(pool_a, pool_b)
+        if g % 9 != 8 and g != 59:                              # now and then no prefetch: the serial path
+            pl.prefetch(best)
+    st = pl.stats()
+    assert st["hits"] + st["misses"] > 40
+    if p_change == 0.0:
+        assert st["misses"] == 0
+    if p_change == 1.0 and P > 3:
+        assert st["misses"] > 0 and st["redrawn_individuals"] > 0
+    # an unused prefetch returns its draws to the stream: both RNGs continue identically
+    pl.prefetch(0)
+    pl.close()
+    assert [b.L.gsgph_rng_intn(b.rng, 1000) for _ in range(50)] == [a.L.gsgph_rng_intn(a.rng, 1000) for _ in range(50)]
+    assert b.L.gsgph_rng_float64(b.rng) == a.L.gsgph_rng_float64(a.rng)
+    a.close(); b.close()
+
+
+def test_planner_rejects_a_second_prefetch():
+    from go_gsgp_b200.host import HostDriver
+    h = HostDriver(population_size=10, nvar=3)
+    pl = h.planner()
+    pl.prefetch(0)
+    with pytest.raises(RuntimeError):
+        pl.prefetch(0)
+    h.close()
