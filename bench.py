@@ -305,7 +305,9 @@ def main():
     # the host's plan builder is pipelined (gsgph_planner_*, include/gsgp_host.h): the next generation's fitness-
     # independent draws (operators, random trees, tournament candidates) are made on a worker thread while the
     # device computes; winners are picked when the fitness arrives.  Same plans and RNG stream as build_plan.
-    planner = host.planner() if os.environ.get("GSGP_BENCH_PLANNER", "1") != "0" else None
+    # With programs=True the worker threads also compile the trees (gsgp_generation_compiled takes them as they are).
+    planner_mode = os.environ.get("GSGP_BENCH_PLANNER", "programs")          # "0": serial gsgph_build_plan, "1": draws only
+    planner = host.planner(programs=planner_mode == "programs") if planner_mode != "0" else None
     def replay_step(count=False):
         nonlocal fit, best, h2d, d2h
         if planner is not None:
@@ -313,7 +315,10 @@ def main():
             planner.prefetch(best)
         else:
             plan, pool = host.build_plan(fit, best)
-        fit, fit_test, best = e.generation(plan, pool)
+        if planner_mode == "programs":
+            fit, fit_test, best = e.generation_compiled(plan, pool, *planner.programs())
+        else:
+            fit, fit_test, best = e.generation(plan, pool)
         if count:
             # uploaded by the call: plan entries, accumulator programs (8 B per function node; a tree of i ints
             # has (i-1)/4 function nodes), program offset/descriptor tables; read back: 2 fitness vectors + best
@@ -399,8 +404,9 @@ def main():
                        "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building",
-                    "plan_builder": ("pipelined (gsgph_planner_*): elite-index guesses right/wrong = %d/%d" %
-                                     (planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)"},
+                    "plan_builder": ("pipelined (gsgph_planner_*%s): elite-index guesses right/wrong = %d/%d" %
+                                     (", trees compiled ahead: gsgp_generation_compiled" if planner_mode == "programs" else "",
+                                      planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)"},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }

@@ -67,6 +67,7 @@ SIGNATURES = {
     "gsgp_eval_initial": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, C.c_int32, _ip, _ip]),
     "gsgp_fitness_all": (C.c_int, [_vp, _dp, _dp, _ip]),
     "gsgp_generation": (C.c_int, [_vp, _vp, _ip, C.c_int32, _dp, _dp, _ip]),
+    "gsgp_generation_compiled": (C.c_int, [_vp, _vp, _ip, C.c_int32, _vp, C.c_int32, _ip, _ip, _dp, _dp, _ip]),
     "gsgp_run_generations": (C.c_int, [_vp, C.c_int32]),
     "gsgp_sync": (C.c_int, [_vp]),
     "gsgp_get_fitness": (C.c_int, [_vp, _dp, _dp, _ip]),

@@ -1279,8 +1279,10 @@ int gsgp_fitness_all(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_
     return read_fitness(c, fit, fit_test, index_best);
 }
 
-int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
-                    double *fit_out, double *fit_test_out, int32_t *index_best_out)
+// gsgp_generation / gsgp_generation_compiled: `programs` == NULL -> the trees are compiled here (staging workers)
+static int generation_impl(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                           const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off, const int32_t *prog_desc_in,
+                           double *fit_out, double *fit_test_out, int32_t *index_best_out)
 {
     if (check_ready(c)) return 1;
     static const bool trace = getenv("GSGP_TRACE") != nullptr;
@@ -1306,6 +1308,54 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
         c->hplan.p[k] = e;
     }
     auto t1 = now();
+    if (programs) {
+        // The caller staged the programs (gsgph_compile_trees / the pipelined planner): check what the kernels rely on
+        // for memory safety -- slot ranges, operand ids, spill levels -- copy into the pinned buffers, upload, launch.
+        if (!prog_off || !prog_desc_in || n_instructions < 0) return fail(c, "null program tables");
+        const uint32_t n_opd = (uint32_t)(c->n_symbols - 4);
+        int32_t max_need = 0;
+        CU(c, c->hprog.reserve((size_t)n_instructions + 1));
+        CU(c, c->ds[0].prog_pool.reserve((size_t)n_instructions + 1));
+        for (int32_t t = 0; t < 2 * P; ++t) {
+            if (len[(size_t)t] <= 0) { c->hoff.p[t] = 0; c->hlen.p[t] = 0; continue; }
+            if (!tree_pool || off[(size_t)t] < 0 || (int64_t)off[(size_t)t] + len[(size_t)t] > pool_len) return fail(c, "tree %d: tree exceeds the tree pool", t);
+            const int32_t d = prog_desc_in[t], n = prog_desc_len(d), need = prog_desc_need(d), o = prog_off[t];
+            if (n < 1 || o < 0 || (int64_t)o + n > n_instructions) return fail(c, "program of tree slot %d outside the program pool", t);
+            if (need > kMaxStackLevels) return fail(c, "program of tree slot %d needs %d spill levels > %d", t, need, kMaxStackLevels);
+            if (n > len[(size_t)t] / 4 + 1) return fail(c, "program of tree slot %d is longer than its tree", t);
+            for (int32_t i = 0; i < n; ++i) {
+                const uint32_t code = programs[2 * (size_t)(o + i)], ab = programs[2 * (size_t)(o + i) + 1];
+                const uint32_t level = code >> kLevelShift, aop = code & 7u;
+                if (aop > (uint32_t)A_MOV || (code & ~((~0u << kLevelShift) | K_LOADA | K_PUSH | K_POP | 7u)) ||
+                    (ab & 0xFFFFu) >= n_opd || (ab >> 16) >= n_opd || level >= (uint32_t)std::max(need, 1))
+                    return fail(c, "program of tree slot %d: bad instruction %d", t, i);
+            }
+            c->hoff.p[t] = o; c->hlen.p[t] = d;
+            max_need = std::max(max_need, need);
+        }
+        if (n_instructions > 0) memcpy(c->hprog.p, programs, sizeof(Ins) * (size_t)n_instructions);
+        c->dcur = 0;
+        CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
+        if (n_instructions > 0)
+            CU(c, cudaMemcpyAsync(c->ds[0].prog_pool.p, c->hprog.p, sizeof(Ins) * (size_t)n_instructions, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->dprog_off, c->hoff.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->ds[0].prog_desc, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
+        if (c->fused) {
+            const double n_cases = (double)(c->L.n_tr + c->L.n_te);
+            if (launch_gen(c, 0, P, 0, c->dsem[c->cur], c->dsem[c->cur ^ 1], gen_bytes(c->hplan.p, 0, P, n_cases))) return 1;
+            if (finish_generation(c)) return 1;
+        } else if (run_generation_kernels(c, c->hplan.p, max_need)) return 1;
+        c->last_plan.assign(plan, plan + P);
+        c->last_pool.assign(tree_pool, tree_pool + std::max(pool_len, 0));
+        auto t2 = now();
+        const int rc = read_fitness(c, fit_out, fit_test_out, index_best_out);
+        if (trace) {
+            auto us = [](auto x, auto y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
+            fprintf(stderr, "gsgp_generation_compiled: validate plan %.0f us, check+upload+launch %.0f, wait+readback %.0f\n",
+                    us(t0, t1), us(t1, t2), us(t2, now()));
+        }
+        return rc;
+    }
     // compile the generation's trees (compile_prefix_tree) on the staging workers, straight into pinned memory.
     // GSGP_REPLAY_CHUNKS > 1 cuts the population into chunks so that staging chunk i+1 overlaps gen_kernel of chunk
     // i; measured slower at config 2 (4 launches: 4 x 0.31 ms vs 0.94 ms, X tiles staged 4 times), so 1 by default.
@@ -1378,6 +1428,21 @@ int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tre
                 us(t0, t1), us(t1, t2), us_stage, us(t3, t4), us(t4, t5), us(t5, now()));
     }
     return rc;
+}
+
+int gsgp_generation(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                    double *fit_out, double *fit_test_out, int32_t *index_best_out)
+{
+    return generation_impl(c, plan, tree_pool, pool_len, nullptr, 0, nullptr, nullptr, fit_out, fit_test_out, index_best_out);
+}
+
+int gsgp_generation_compiled(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                             const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off,
+                             const int32_t *prog_desc, double *fit_out, double *fit_test_out, int32_t *index_best_out)
+{
+    if (check_ready(c)) return 1;
+    if (!programs) return fail(c, "null programs");
+    return generation_impl(c, plan, tree_pool, pool_len, programs, n_instructions, prog_off, prog_desc, fit_out, fit_test_out, index_best_out);
 }
 
 int gsgp_run_generations(gsgp_ctx *c, int32_t n)

@@ -188,17 +188,45 @@ int32_t tournament(gsgph_rng *r, const gsgph_params *p, const double *fit)      
 }
 
 
-// individuals [k_from, P) of one generation's decisions (:1447-1470), drawn in the reference's order.
-// Returns true when the tree pool is too small.
-bool build_range(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t index_best, int32_t k_from,
-                 gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t &used_io)
-{
-    TreeBuilder tb{r, p, {}};
-    bool overflow = false;
-    int32_t used = used_io;
-    const int64_t tree_max = p->max_depth_creation < 20 ? ((int64_t)4 << p->max_depth_creation) : INT32_MAX;
-    auto new_tree = [&](int32_t &off, int32_t &len) {
-        if (used + tree_max <= cap) {                                          // room for any tree: built in place
+// Where the interpreter programs of a plan's trees go when the host stages them itself (gsgp_generation_compiled)
+struct ProgSink {
+    gsgp::Ins *ins = nullptr;
+    int32_t cap = 0, used = 0;
+    int32_t *off = nullptr, *desc = nullptr;                    // per tree slot 2*k + which
+    int32_t n_symbols = 0;
+    std::vector<uint8_t> need;
+    std::vector<gsgp::TreeFrame> frames;
+    static int32_t n_ins_of(int32_t tree_len) { return tree_len <= 0 ? 0 : tree_len == 1 ? 1 : (tree_len - 1) / 4; }
+    bool compile(int32_t slot, const int32_t *tree, int32_t len, int32_t at)      // false: not a tree
+    {
+        int n = 0, nd = 0;
+        const char *err = "";
+        if (!gsgp::compile_prefix_tree(tree, len, n_symbols, ins + at, n, nd, need, frames, err) || n != n_ins_of(len)) return false;
+        off[slot] = at; desc[slot] = gsgp::prog_desc(n, nd);
+        return true;
+    }
+};
+
+// One generation's decisions (:1447-1470), individual by individual in the reference's draw order.
+struct PlanWriter {
+    gsgph_rng *r;
+    const gsgph_params *p;
+    const double *fit;
+    int32_t index_best;
+    gsgp_plan_entry *plan;
+    int32_t *pool;
+    int32_t cap, used = 0;
+    bool overflow = false;                                      // the tree pool is too small
+    TreeBuilder tb;
+    int64_t tree_max;
+    ProgSink *sink = nullptr;                                   // optional: compile each tree as it is drawn
+    PlanWriter(gsgph_rng *r_, const gsgph_params *p_, const double *fit_, int32_t best, gsgp_plan_entry *plan_,
+               int32_t *pool_, int32_t cap_, int32_t used_)
+        : r(r_), p(p_), fit(fit_), index_best(best), plan(plan_), pool(pool_), cap(cap_), used(used_), tb{r_, p_, {}},
+          tree_max(p_->max_depth_creation < 20 ? ((int64_t)4 << p_->max_depth_creation) : INT32_MAX) {}
+    void new_tree(int32_t &off, int32_t &len)
+    {
+        if (used + tree_max <= cap) {                           // room for any tree: built in place
             off = used; len = grow_tree_array(r, p, pool + used); used += len;
             return;
         }
@@ -206,8 +234,26 @@ bool build_range(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t
         if (used + (int64_t)t.size() > cap) { overflow = true; off = -1; len = 0; return; }
         memcpy(pool + used, t.data(), t.size() * sizeof(int32_t));
         off = used; len = (int32_t)t.size(); used += len;
-    };
-    for (int32_t k = k_from; k < p->population_size; ++k) {
+    }
+    void compile_trees_of(int32_t k)
+    {
+        const gsgp_plan_entry &e = plan[k];
+        const int32_t off[2] = {e.tree0_off, e.tree1_off}, len[2] = {e.tree0_len, e.tree1_len};
+        for (int w = 0; w < 2; ++w) {
+            sink->off[2 * k + w] = 0; sink->desc[2 * k + w] = 0;
+            if (len[w] <= 0 || overflow) continue;
+            if (sink->used + ProgSink::n_ins_of(len[w]) > sink->cap) { overflow = true; continue; }
+            sink->compile(2 * k + w, pool + off[w], len[w], sink->used);
+            sink->used += ProgSink::n_ins_of(len[w]);
+        }
+    }
+    void one(int32_t k)
+    {
+        draw_one(k);
+        if (sink) compile_trees_of(k);
+    }
+    void draw_one(int32_t k)
+    {
         gsgp_plan_entry &e = plan[k];
         e.op = GSGP_OP_REPR; e.elite = (k == index_best); e.p1 = -1; e.p2 = -1;
         e.tree0_off = -1; e.tree0_len = 0; e.tree1_off = -1; e.tree1_len = 0; e.ms = 0.0;
@@ -231,11 +277,12 @@ bool build_range(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t
             e.op = GSGP_OP_REPR;                                                // :1467-1469
             e.p1 = (k != index_best) ? tournament(r, p, fit) : k;
         }
-        if (overflow) break;
     }
-    used_io = used;
-    return overflow;
-}
+    void range(int32_t k_from)
+    {
+        for (int32_t k = k_from; k < p->population_size && !overflow; ++k) one(k);
+    }
+};
 
 }  // namespace
 
@@ -303,10 +350,10 @@ int gsgph_initialize_population(gsgph_rng *r, const gsgph_params *p, int32_t n_s
 int gsgph_build_plan(gsgph_rng *r, const gsgph_params *p, const double *fit, int32_t index_best,
                      gsgp_plan_entry *plan, int32_t *pool, int32_t cap, int32_t *pool_len)
 {
-    int32_t used = 0;
-    const bool overflow = build_range(r, p, fit, index_best, 0, plan, pool, cap, used);
-    if (pool_len) *pool_len = used;
-    return overflow ? 1 : 0;
+    PlanWriter w(r, p, fit, index_best, plan, pool, cap, 0);
+    w.range(0);
+    if (pool_len) *pool_len = w.used;
+    return w.overflow ? 1 : 0;
 }
 
 int gsgph_build_effects_plan(gsgph_rng *r, const gsgph_params *p, int32_t test_crossover,
@@ -351,22 +398,38 @@ int32_t gsgph_best_individual(const gsgph_params *p, const double *fit)
 // ---- pipelined planner ------------------------------------------------------------------------------------------
 // gsgph_build_plan is serial with the device: generation g+1's plan needs generation g's fitness.  But only the
 // tournament WINNERS need fitness values; the operator draw, the random trees, the mutation step and the tournament
-// CANDIDATES need nothing but the RNG -- and the elite index (the elite slot skips its draws, :847,:877,:918).  The
-// elite keeps its index unless a strictly better child appears, so the planner draws generation g+1 on a worker
-// thread while the device computes generation g, guessing the elite, and finishes the plan when the fitness arrives:
-// winners among the recorded candidates, and -- when the guess was wrong -- individuals from the first differing slot
-// on redrawn from the recorded raw RNG values (gsgph_rng's tape), so the plan and the RNG stream are exactly those
-// gsgph_build_plan would have produced.
+// CANDIDATES need nothing but the RNG -- and the elite index (the elite slot skips its draws, :847,:877,:918).  So the
+// planner draws generation g+1 on a worker thread while the device computes generation g, under a guess of the elite
+// index, and finishes the plan when the fitness arrives: winners among the recorded candidates and, when the guess
+// was wrong, a repair.  The repair re-reads the recorded raw RNG values (gsgph_rng's queue) from the first slot whose
+// draws change.  Past that slot the individuals parse a SHIFTED stream -- until an individual happens to start at a
+// raw position where some individual of the draft started: from there on the draft's parse is the right one again
+// (same values, same order) and its entries are copied, shifted by the index difference, up to the next slot that
+// differs (the other elite index).  A wrong guess therefore costs a few dozen re-drawn individuals, not the suffix.
+// Plans, tree pools and the RNG stream are exactly those of gsgph_build_plan.
 struct gsgph_planner {
     gsgph_rng *r;
     gsgph_params p;
-    struct Rec { size_t tape_pos; int32_t pool_used; int32_t ncand; };      // per individual: where its draws start
-    std::vector<Rec> rec;
+    struct Rec { size_t pos; int32_t pool_used; int32_t ncand; };           // per draft individual: where its draws / trees start
+    std::vector<Rec> rec;                                                   // P + 1: the last entry is the draft's end
     std::vector<int32_t> cand;                                              // [P][2][tournament_size]
-    std::vector<gsgp_plan_entry> plan[2];
-    std::vector<int32_t> pool[2];                                           // grown on demand up to pool_max
+    struct Buf {
+        std::vector<gsgp_plan_entry> plan; std::vector<int32_t> pool;
+        std::vector<gsgp::Ins> prog; std::vector<int32_t> prog_off, prog_desc; int32_t n_ins = 0;    // with programs enabled
+    } buf[3];
     size_t pool_max = 0;
-    int cur = 0;                                                            // buffers the last gsgph_planner_plan returned
+    // programs (gsgph_planner_enable_programs): the draft's trees are compiled on the worker + helper threads
+    bool programs = false;
+    int32_t n_symbols = 0;
+    std::vector<int32_t> prog_start;                                        // P + 1: instructions before draft individual k
+    std::vector<std::thread> helpers;
+    std::vector<ProgSink> sinks;                                            // per compile thread (scratch) + [n] for the caller's thread
+    uint64_t job_epoch = 0;
+    int job_pending = 0;
+    bool job_quit = false;
+    std::mutex jmu;
+    std::condition_variable jcv, jdone;
+    int out = 0, draft = 1;                                                 // buffers: last result (the caller reads it), draft
     int32_t guess = -1, used = 0;
     bool pending = false, overflow = false;
     int64_t hits = 0, misses = 0, redrawn = 0;
@@ -386,51 +449,101 @@ struct gsgph_planner {
             if (better(&p, fit[c[i]], fit[best])) best = c[i];
         return best;
     }
+    void size_pool(int b, size_t n)
+    {
+        buf[b].pool.resize(n);
+        if (programs) buf[b].prog.resize(n / 4 + 2 * (size_t)p.population_size + 16);   // one instruction per function node
+    }
     bool grow_pool(int b)                                                   // false: already at the worst-case size
     {
-        if (pool[b].size() >= pool_max) return false;
-        pool[b].resize(std::min(pool_max, pool[b].size() * 2));
+        if (buf[b].pool.size() >= pool_max) return false;
+        size_pool(b, std::min(pool_max, buf[b].pool.size() * 2));
         return true;
     }
-    // everything of one generation that does not need fitness values, into the buffers `cur ^ 1`
+    ProgSink *sink_for(int b, ProgSink &s)                                  // the caller thread's sink onto buffer b
+    {
+        if (!programs) return nullptr;
+        s.ins = buf[b].prog.data(); s.cap = (int32_t)buf[b].prog.size(); s.used = 0;
+        s.off = buf[b].prog_off.data(); s.desc = buf[b].prog_desc.data(); s.n_symbols = n_symbols;
+        return &s;
+    }
+    // the draft's trees -> programs, in place at offsets known from the tree lengths; individuals split over the threads
+    void compile_part(int part, int parts)
+    {
+        const int32_t P = p.population_size;
+        Buf &B = buf[draft];
+        ProgSink &s = sinks[(size_t)part];
+        s.ins = B.prog.data(); s.off = B.prog_off.data(); s.desc = B.prog_desc.data(); s.n_symbols = n_symbols;
+        const int32_t k0 = (int32_t)((int64_t)P * part / parts), k1 = (int32_t)((int64_t)P * (part + 1) / parts);
+        for (int32_t k = k0; k < k1; ++k) {
+            const gsgp_plan_entry &e = B.plan[(size_t)k];
+            int32_t at = prog_start[(size_t)k];
+            if (e.tree0_len > 0) { s.compile(2 * k, B.pool.data() + e.tree0_off, e.tree0_len, at); at += ProgSink::n_ins_of(e.tree0_len); }
+            if (e.tree1_len > 0) s.compile(2 * k + 1, B.pool.data() + e.tree1_off, e.tree1_len, at);
+        }
+    }
+    void compile_draft()
+    {
+        const int32_t P = p.population_size;
+        Buf &B = buf[draft];
+        int32_t acc = 0;
+        for (int32_t k = 0; k < P; ++k) {
+            prog_start[(size_t)k] = acc;
+            B.prog_off[2 * (size_t)k] = B.prog_off[2 * (size_t)k + 1] = 0;
+            B.prog_desc[2 * (size_t)k] = B.prog_desc[2 * (size_t)k + 1] = 0;
+            acc += ProgSink::n_ins_of(B.plan[(size_t)k].tree0_len) + ProgSink::n_ins_of(B.plan[(size_t)k].tree1_len);
+        }
+        prog_start[(size_t)P] = acc;
+        B.n_ins = acc;
+        const int parts = (int)helpers.size() + 1;
+        if (parts > 1 && P >= 256) {
+            { std::lock_guard<std::mutex> lk(jmu); job_pending = parts - 1; ++job_epoch; }
+            jcv.notify_all();
+            compile_part(0, parts);
+            std::unique_lock<std::mutex> lk(jmu);
+            jdone.wait(lk, [&] { return job_pending == 0; });
+        } else compile_part(0, 1);
+    }
+    void helper_loop(int part)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(jmu);
+                jcv.wait(lk, [&] { return job_epoch != seen || job_quit; });
+                if (job_quit) return;
+                seen = job_epoch;
+            }
+            compile_part(part, (int)helpers.size() + 1);
+            { std::lock_guard<std::mutex> lk(jmu); if (--job_pending == 0) jdone.notify_one(); }
+        }
+    }
+    // everything of one generation that does not need fitness values, into the draft buffers
     void draw()
     {
         r->tape_begin();
         for (;;) {
             draw_once();
-            if (!overflow || !grow_pool(cur ^ 1)) return;
-            r->seek(0);                                                    // same raw values, larger pool
+            if (!overflow || !grow_pool(draft)) break;
+            r->seek(0);                                                     // same raw values, larger pool
         }
+        if (programs && !overflow) compile_draft();
     }
     void draw_once()
     {
-        gsgp_plan_entry *pl = plan[cur ^ 1].data();
-        int32_t *po = pool[cur ^ 1].data();
-        const int32_t cap = (int32_t)pool[cur ^ 1].size(), ts = p.tournament_size;
-        TreeBuilder tb{r, &p, {}};
-        used = 0; overflow = false;
-        const int64_t tree_max = p.max_depth_creation < 20 ? ((int64_t)4 << p.max_depth_creation) : INT32_MAX;
-        auto new_tree = [&](int32_t &off, int32_t &len) {
-            if (used + tree_max <= cap) {
-                off = used; len = grow_tree_array(r, &p, po + used); used += len;
-                return;
-            }
-            const std::vector<int32_t> &t = tb.build(p.max_depth_creation, 0);
-            if (used + (int64_t)t.size() > cap) { overflow = true; off = -1; len = 0; return; }
-            memcpy(po + used, t.data(), t.size() * sizeof(int32_t));
-            off = used; len = (int32_t)t.size(); used += len;
-        };
-        for (int32_t k = 0; k < p.population_size && !overflow; ++k) {
-            gsgp_plan_entry &e = pl[k];
+        const int32_t P = p.population_size, ts = p.tournament_size;
+        PlanWriter w(r, &p, nullptr, guess, buf[draft].plan.data(), buf[draft].pool.data(), (int32_t)buf[draft].pool.size(), 0);
+        for (int32_t k = 0; k < P && !w.overflow; ++k) {
+            gsgp_plan_entry &e = w.plan[k];
             int32_t *c = cand.data() + (size_t)k * 2 * ts;
-            rec[(size_t)k] = {r->tell(), used, 0};
+            rec[(size_t)k] = {r->tell(), w.used, 0};
             e.op = GSGP_OP_REPR; e.elite = (k == guess); e.p1 = k; e.p2 = -1;
             e.tree0_off = -1; e.tree0_len = 0; e.tree1_off = -1; e.tree1_len = 0; e.ms = 0.0;
             const double rand_num = r->float64();                                   // :1451
             if (rand_num < p.p_crossover) {                                         // :1453
                 e.op = GSGP_OP_XO;
                 if (e.elite) continue;
-                new_tree(e.tree0_off, e.tree0_len);                                 // :879
+                w.new_tree(e.tree0_off, e.tree0_len);                               // :879
                 draw_candidates(c); draw_candidates(c + ts);                        // :881-882
                 rec[(size_t)k].ncand = 2;
             } else if (rand_num < p.p_crossover + p.p_mutation) {                   // :1459
@@ -439,14 +552,86 @@ struct gsgph_planner {
                 draw_candidates(c);                                                 // :847-850
                 rec[(size_t)k].ncand = 1;
                 e.ms = r->float64();                                                // :919
-                new_tree(e.tree0_off, e.tree0_len);                                 // :921
-                new_tree(e.tree1_off, e.tree1_len);                                 // :922
+                w.new_tree(e.tree0_off, e.tree0_len);                               // :921
+                w.new_tree(e.tree1_off, e.tree1_len);                               // :922
             } else {
                 if (e.elite) continue;                                              // :1467-1469
                 draw_candidates(c);
                 rec[(size_t)k].ncand = 1;
             }
         }
+        rec[(size_t)P] = {r->tell(), w.used, 0};
+        used = w.used; overflow = w.overflow;
+    }
+    void resolve(gsgp_plan_entry &e, int32_t k_draft, const double *fit) const
+    {
+        const int32_t *c = cand.data() + (size_t)k_draft * 2 * p.tournament_size;
+        const int32_t n = rec[(size_t)k_draft].ncand;
+        if (n >= 1) e.p1 = winner(c, fit);
+        if (n == 2) e.p2 = winner(c + p.tournament_size, fit);
+    }
+    // the draft was drawn for elite index `guess`, the elite is `best`: the plan for `best` into buffer b.
+    // Returns true when b's tree pool is too small.
+    bool repair(int b, const double *fit, int32_t best)
+    {
+        const int32_t P = p.population_size;
+        const gsgp_plan_entry *dplan = buf[draft].plan.data();
+        const int32_t *dpool = buf[draft].pool.data();
+        const int32_t m = std::max(0, std::min(best, guess));               // slots before m: draws unchanged
+        PlanWriter w(r, &p, fit, best, buf[b].plan.data(), buf[b].pool.data(), (int32_t)buf[b].pool.size(), 0);
+        ProgSink &sk = sinks.back();
+        w.sink = sink_for(b, sk);
+        auto copy_run = [&](int32_t k, int32_t kd, int32_t n) {             // draft slots [kd, kd+n) become slots [k, k+n)
+            const int32_t u0 = rec[(size_t)kd].pool_used, u1 = rec[(size_t)(kd + n)].pool_used, shift = w.used - u0;
+            if ((int64_t)w.used + (u1 - u0) > w.cap) { w.overflow = true; return; }
+            memcpy(w.pool + w.used, dpool + u0, sizeof(int32_t) * (size_t)(u1 - u0));
+            memcpy(w.plan + k, dplan + kd, sizeof(gsgp_plan_entry) * (size_t)n);
+            for (int32_t i = 0; i < n; ++i) {
+                gsgp_plan_entry &e = w.plan[k + i];
+                if (e.tree0_len) e.tree0_off += shift;
+                if (e.tree1_len) e.tree1_off += shift;
+                resolve(e, kd + i, fit);
+            }
+            w.used += u1 - u0;
+            if (w.sink) {                                                   // the run's programs, shifted the same way
+                const int32_t q0 = prog_start[(size_t)kd], q1 = prog_start[(size_t)(kd + n)], qshift = sk.used - q0;
+                if (sk.used + (q1 - q0) > sk.cap) { w.overflow = true; return; }
+                memcpy(sk.ins + sk.used, buf[draft].prog.data() + q0, sizeof(gsgp::Ins) * (size_t)(q1 - q0));
+                const int32_t *doff = buf[draft].prog_off.data(), *ddesc = buf[draft].prog_desc.data();
+                for (int32_t t = 0; t < 2 * n; ++t) {
+                    const int32_t d = ddesc[2 * kd + t];
+                    sk.desc[2 * k + t] = d;
+                    sk.off[2 * k + t] = d ? doff[2 * kd + t] + qshift : 0;
+                }
+                sk.used += q1 - q0;
+            }
+        };
+        copy_run(0, 0, m);
+        int32_t k = m, kd = m;
+        r->seek(rec[(size_t)m].pos);
+        while (k < P && !w.overflow) {
+            const size_t pos = r->tell();
+            while (kd < P && rec[(size_t)kd].pos < pos) ++kd;
+            // a run of draft individuals that parse identically here: it starts at this raw position, holds neither
+            // the guessed elite (its draft skipped the draws) nor -- at its new index -- the actual one
+            int32_t n = 0;
+            if (kd < P && rec[(size_t)kd].pos == pos) {
+                n = std::min(P - k, P - kd);
+                if (guess >= kd) n = std::min(n, guess - kd);
+                if (best >= k) n = std::min(n, best - k);
+            }
+            if (n > 0) {
+                copy_run(k, kd, n);
+                k += n; kd += n;
+                r->seek(rec[(size_t)kd].pos);
+            } else {
+                w.one(k++);
+                ++redrawn;
+            }
+        }
+        used = w.used;
+        if (w.sink) buf[b].n_ins = sk.used;
+        return w.overflow;
     }
     void loop()
     {
@@ -470,12 +655,45 @@ gsgph_planner *gsgph_planner_new(gsgph_rng *r, const gsgph_params *p)
     pl->r = r; pl->p = *p;
     const size_t P = (size_t)p->population_size;
     const size_t tree_cap = ((size_t)4 << p->max_depth_creation);           // a depth-d tree has at most 4*2^d - 3 ints
-    pl->rec.resize(P);
+    pl->rec.resize(P + 1);
     pl->cand.resize(P * 2 * (size_t)p->tournament_size);
     pl->pool_max = std::min<size_t>(2 * P * tree_cap, (size_t)INT32_MAX);
-    for (int b = 0; b < 2; ++b) { pl->plan[b].resize(P); pl->pool[b].resize(std::min<size_t>(pl->pool_max, 64 * P + 1024)); }
+    for (auto &b : pl->buf) { b.plan.resize(P); b.pool.resize(std::min<size_t>(pl->pool_max, 64 * P + 2 * tree_cap)); }
+    pl->sinks.resize(1);
     pl->worker = std::thread([pl] { pl->loop(); });
     return pl;
+}
+
+int gsgph_planner_enable_programs(gsgph_planner *pl, int32_t n_threads)
+{
+    if (!pl) return 1;
+    if (pl->programs) return 0;
+    if (pl->pending) return 2;                                              // before the first prefetch
+    const size_t P = (size_t)pl->p.population_size;
+    pl->programs = true;
+    pl->n_symbols = kFunc + pl->p.nvar + pl->p.num_constants;
+    pl->prog_start.resize(P + 1);
+    for (int b = 0; b < 3; ++b) {
+        pl->buf[b].prog_off.assign(2 * P, 0); pl->buf[b].prog_desc.assign(2 * P, 0);
+        pl->size_pool(b, pl->buf[b].pool.size());
+    }
+    if (n_threads <= 0) n_threads = std::max(1, std::min(4, (int)std::thread::hardware_concurrency() / 4));
+    n_threads = std::min(n_threads, 16);
+    pl->sinks.resize((size_t)n_threads + 1);
+    for (int i = 1; i < n_threads; ++i) pl->helpers.emplace_back([pl, i] { pl->helper_loop(i); });
+    return 0;
+}
+
+int gsgph_planner_programs(const gsgph_planner *pl, const uint32_t **programs, int32_t *n_instructions,
+                           const int32_t **prog_off, const int32_t **prog_desc)
+{
+    if (!pl || !pl->programs) return 1;
+    const gsgph_planner::Buf &B = pl->buf[pl->out];
+    if (programs) *programs = reinterpret_cast<const uint32_t *>(B.prog.data());
+    if (n_instructions) *n_instructions = B.n_ins;
+    if (prog_off) *prog_off = B.prog_off.data();
+    if (prog_desc) *prog_desc = B.prog_desc.data();
+    return 0;
 }
 
 static void planner_wait(gsgph_planner *pl)
@@ -494,8 +712,14 @@ void gsgph_planner_free(gsgph_planner *pl)
     }
     pl->cv.notify_all();
     pl->worker.join();
+    {
+        std::lock_guard<std::mutex> lk(pl->jmu);
+        pl->job_quit = true;
+    }
+    pl->jcv.notify_all();
+    for (auto &t : pl->helpers) t.join();
     // a prefetched generation that was never asked for: its draws go back to the stream
-    if (pl->pending) pl->r->seek(pl->rec[0].tape_pos);
+    if (pl->pending) pl->r->seek(pl->rec[0].pos);
     pl->r->recording = false;
     delete pl;
 }
@@ -506,6 +730,7 @@ int gsgph_planner_prefetch(gsgph_planner *pl, int32_t index_best_guess)
     planner_wait(pl);
     if (pl->pending) return 2;                                              // one generation ahead, not more
     pl->guess = index_best_guess;
+    pl->draft = (pl->out + 1) % 3;
     pl->pending = true;
     {
         std::lock_guard<std::mutex> lk(pl->mu);
@@ -520,45 +745,75 @@ int gsgph_planner_plan(gsgph_planner *pl, const double *fit, int32_t index_best,
 {
     if (!pl || !fit) return 1;
     planner_wait(pl);
-    const int32_t P = pl->p.population_size, ts = pl->p.tournament_size;
-    const int nxt = pl->cur ^ 1;
-    gsgp_plan_entry *plan = pl->plan[nxt].data();
+    const int32_t P = pl->p.population_size;
     bool overflow = false;
-    // individuals [m, P) drawn serially with the fitness at hand, from the raw values at tape position pos on
-    auto serial_from = [&](int32_t m, size_t pos, int32_t used0) {
-        for (;;) {
-            pl->r->seek(pos);
-            int32_t used = used0;
-            overflow = build_range(pl->r, &pl->p, fit, index_best, m, plan, pl->pool[nxt].data(), (int32_t)pl->pool[nxt].size(), used);
-            pl->used = used;
-            if (!overflow || !pl->grow_pool(nxt)) return;
-        }
-    };
+    int res;
     if (!pl->pending) {                                                     // nothing prefetched: the plain serial build
+        res = (pl->out + 1) % 3;
         pl->r->tape_begin();
-        serial_from(0, 0, 0);
-    } else {
-        pl->pending = false;
-        overflow = pl->overflow;                                            // only at the worst-case pool size
-        const int32_t m = overflow ? P : (index_best == pl->guess ? P : std::max(0, std::min(index_best, pl->guess)));
-        for (int32_t k = 0; k < m; ++k) {                                   // winners among the drawn candidates
-            const gsgph_planner::Rec &rc = pl->rec[(size_t)k];
-            const int32_t *c = pl->cand.data() + (size_t)k * 2 * ts;
-            if (rc.ncand >= 1) plan[k].p1 = pl->winner(c, fit);
-            if (rc.ncand == 2) plan[k].p2 = pl->winner(c + ts, fit);
+        for (;;) {
+            pl->r->seek(0);
+            PlanWriter w(pl->r, &pl->p, fit, index_best, pl->buf[res].plan.data(), pl->buf[res].pool.data(), (int32_t)pl->buf[res].pool.size(), 0);
+            w.sink = pl->sink_for(res, pl->sinks.back());
+            w.range(0);
+            pl->used = w.used; overflow = w.overflow;
+            if (w.sink) pl->buf[res].n_ins = w.sink->used;
+            if (!overflow || !pl->grow_pool(res)) break;
         }
-        if (m < P) {                                                        // wrong guess: slots m.. consume the same raw values again
-            serial_from(m, pl->rec[(size_t)m].tape_pos, pl->rec[(size_t)m].pool_used);
-            ++pl->misses; pl->redrawn += P - m;
-        } else if (!overflow) ++pl->hits;
+    } else if (pl->overflow) {                                              // only at the worst-case pool size
+        pl->pending = false;
+        res = pl->draft; overflow = true;
+    } else if (index_best == pl->guess) {                                   // right guess: winners among the drawn candidates
+        pl->pending = false;
+        res = pl->draft;
+        gsgp_plan_entry *plan = pl->buf[res].plan.data();
+        for (int32_t k = 0; k < P; ++k) pl->resolve(plan[k], k, fit);
+        ++pl->hits;
+    } else {                                                                // wrong guess: repaired into the third buffer
+        pl->pending = false;
+        res = 3 - pl->out - pl->draft;
+        const int32_t draft_used = pl->used;
+        for (;;) {
+            overflow = pl->repair(res, fit, index_best);
+            if (!overflow || !pl->grow_pool(res)) break;
+            pl->used = draft_used;
+        }
+        ++pl->misses;
     }
-    const int32_t *pool = pl->pool[nxt].data();
     pl->r->recording = false;
-    pl->cur = nxt;
-    if (plan_out) *plan_out = plan;
-    if (pool_out) *pool_out = pool;
+    pl->out = res;
+    if (plan_out) *plan_out = pl->buf[res].plan.data();
+    if (pool_out) *pool_out = pl->buf[res].pool.data();
     if (pool_len) *pool_len = pl->used;
     return overflow ? 3 : 0;
+}
+
+int gsgph_compile_plan(const gsgp_plan_entry *plan, int32_t population_size, const int32_t *tree_pool, int32_t pool_len,
+                       int32_t n_symbols, uint32_t *programs, int32_t cap, int32_t *n_instructions, int32_t *prog_off,
+                       int32_t *prog_desc)
+{
+    if (!plan || !programs || !prog_off || !prog_desc || population_size < 0) return 1;
+    ProgSink s;
+    s.ins = reinterpret_cast<gsgp::Ins *>(programs); s.cap = cap; s.off = prog_off; s.desc = prog_desc; s.n_symbols = n_symbols;
+    for (int32_t k = 0; k < population_size; ++k) {
+        const gsgp_plan_entry &e = plan[k];
+        const bool computed = !e.elite && (e.op == GSGP_OP_XO || e.op == GSGP_OP_MUT);
+        const int32_t off[2] = {e.tree0_off, e.tree1_off};
+        const int32_t len[2] = {computed ? e.tree0_len : 0, computed && e.op == GSGP_OP_MUT ? e.tree1_len : 0};
+        for (int w = 0; w < 2; ++w) {
+            prog_off[2 * k + w] = 0; prog_desc[2 * k + w] = 0;
+            if (len[w] <= 0) continue;
+            if (!tree_pool || off[w] < 0 || (int64_t)off[w] + len[w] > pool_len) return 2;
+            if ((int64_t)s.used + len[w] / 4 + 1 > cap) return 3;
+            int n = 0, nd = 0;
+            const char *err = "";
+            if (!gsgp::compile_prefix_tree(tree_pool + off[w], len[w], n_symbols, s.ins + s.used, n, nd, s.need, s.frames, err)) return 2;
+            prog_off[2 * k + w] = s.used; prog_desc[2 * k + w] = gsgp::prog_desc(n, nd);
+            s.used += n;
+        }
+    }
+    if (n_instructions) *n_instructions = s.used;
+    return 0;
 }
 
 void gsgph_planner_stats(const gsgph_planner *pl, int64_t *hits, int64_t *misses, int64_t *redrawn)

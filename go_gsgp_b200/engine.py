@@ -157,6 +157,23 @@ class Engine:
                                         capi.dptr(fit), capi.dptr(fit_test), C.byref(best)))
         return fit, fit_test, best.value
 
+    def generation_compiled(self, plan, tree_pool, programs, prog_off, prog_desc):
+        """gsgp_generation_compiled: the trees arrive already compiled (HostDriver.compile_plan / Planner.programs)"""
+        plan = np.ascontiguousarray(plan)
+        assert plan.dtype == PLAN_DTYPE and len(plan) == self.P
+        pool = np.ascontiguousarray(tree_pool, np.int32)
+        if len(pool) == 0:
+            pool = np.zeros(1, np.int32)
+        programs = np.ascontiguousarray(programs, np.uint32)
+        prog_off, prog_desc = np.ascontiguousarray(prog_off, np.int32), np.ascontiguousarray(prog_desc, np.int32)
+        assert len(prog_off) == 2 * self.P and len(prog_desc) == 2 * self.P and len(programs) % 2 == 0
+        fit, fit_test, best = np.empty(self.P), np.empty(self.P), C.c_int32()
+        self._ck(self.L.gsgp_generation_compiled(self.h, plan.ctypes.data, capi.iptr(pool), len(pool),
+                                                 programs.ctypes.data if len(programs) else pool.ctypes.data, len(programs) // 2,
+                                                 capi.iptr(prog_off), capi.iptr(prog_desc),
+                                                 capi.dptr(fit), capi.dptr(fit_test), C.byref(best)))
+        return fit, fit_test, best.value
+
     def run_generations(self, n):
         self._ck(self.L.gsgp_run_generations(self.h, n))
 

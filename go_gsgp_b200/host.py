@@ -36,6 +36,11 @@ HOST_SIGNATURES = {
     "gsgph_planner_prefetch": (C.c_int, [C.c_void_p, C.c_int32]),
     "gsgph_planner_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_void_p),
                                      C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
+    "gsgph_planner_enable_programs": (C.c_int, [C.c_void_p, C.c_int32]),
+    "gsgph_planner_programs": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int32),
+                                         C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]),
+    "gsgph_compile_plan": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32),
+                                     C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gsgph_planner_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gsgph_build_effects_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.c_void_p,
                                            C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
@@ -159,15 +164,29 @@ class LineWriter:
 class Planner:
     """gsgph_planner_*: build_plan's result with the fitness-independent draws made on a worker thread while the
     device computes the previous generation.  plan(fit, best) -> (plan, pool) views valid until the next plan();
-    prefetch(best) starts the following generation's draws."""
+    prefetch(best) starts the following generation's draws.  With programs=True the trees are also compiled ahead
+    of time; programs() returns what Engine.generation_compiled takes."""
 
-    def __init__(self, driver: "HostDriver"):
+    def __init__(self, driver: "HostDriver", programs=False, n_threads=0):
         self.L = driver.L
         self.driver = driver                                     # keeps the rng alive
         self.h = self.L.gsgph_planner_new(driver.rng, C.byref(driver.p))
         if not self.h:
             raise ValueError("gsgph_planner_new: bad parameters")
         self.P = driver.P
+        self._views = {}                                         # the planner rotates three buffers: views by address
+        if programs and self.L.gsgph_planner_enable_programs(self.h, n_threads):
+            raise RuntimeError("gsgph_planner_enable_programs failed")
+
+    def _view(self, addr, ctype, count, dtype):
+        key = (addr, count)
+        v = self._views.get(key)
+        if v is None:
+            if len(self._views) > 64:
+                self._views.clear()
+            v = np.frombuffer((ctype * count).from_address(addr), dtype=dtype) if count else np.zeros(0, dtype)
+            self._views[key] = v
+        return v
 
     def plan(self, fit, index_best):
         fit = np.ascontiguousarray(fit, np.float64)
@@ -175,9 +194,19 @@ class Planner:
         rc = self.L.gsgph_planner_plan(self.h, capi.dptr(fit), int(index_best), C.byref(plan_p), C.byref(pool_p), C.byref(n))
         if rc:
             raise RuntimeError(f"gsgph_planner_plan failed ({rc})")
-        plan = np.frombuffer((C.c_char * (PLAN_DTYPE.itemsize * self.P)).from_address(plan_p.value), dtype=PLAN_DTYPE)
-        pool = np.ctypeslib.as_array(pool_p, shape=(max(n.value, 1),))
+        plan = self._view(plan_p.value, C.c_char, PLAN_DTYPE.itemsize * self.P, PLAN_DTYPE)
+        pool = self._view(C.addressof(pool_p.contents), C.c_int32, max(n.value, 1), np.int32)
         return plan, pool
+
+    def programs(self):
+        """(programs uint32[2*n], prog_off int32[2P], prog_desc int32[2P]) of the plan returned last"""
+        pr, n = C.POINTER(C.c_uint32)(), C.c_int32()
+        off, desc = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        if self.L.gsgph_planner_programs(self.h, C.byref(pr), C.byref(n), C.byref(off), C.byref(desc)):
+            raise RuntimeError("planner was created without programs=True")
+        return (self._view(C.addressof(pr.contents), C.c_uint32, 2 * max(n.value, 1), np.uint32)[: 2 * n.value],
+                self._view(C.addressof(off.contents), C.c_int32, 2 * self.P, np.int32),
+                self._view(C.addressof(desc.contents), C.c_int32, 2 * self.P, np.int32))
 
     def prefetch(self, index_best_guess):
         rc = self.L.gsgph_planner_prefetch(self.h, int(index_best_guess))
@@ -258,10 +287,22 @@ class HostDriver:
             raise RuntimeError("gsgph_build_plan: tree pool overflow")
         return self._plan, self._pool[: max(used.value, 1)]
 
-    def planner(self) -> Planner:
-        pl = Planner(self)
+    def planner(self, programs=False, n_threads=0) -> Planner:
+        pl = Planner(self, programs, n_threads)
         self.__dict__.setdefault("_planners", []).append(pl)
         return pl
+
+    def compile_plan(self, plan, pool):
+        """gsgph_compile_plan: (programs, prog_off, prog_desc) for Engine.generation_compiled"""
+        pool = np.ascontiguousarray(pool, np.int32)
+        cap = len(pool) // 4 + 2 * self.P + 1
+        prog, n = np.zeros(2 * cap, np.uint32), C.c_int32()
+        off, desc = np.zeros(2 * self.P, np.int32), np.zeros(2 * self.P, np.int32)
+        rc = self.L.gsgph_compile_plan(plan.ctypes.data, self.P, capi.iptr(pool), len(pool), 4 + self.p.nvar + self.p.num_constants,
+                                       prog.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(n), capi.iptr(off), capi.iptr(desc))
+        if rc:
+            raise ValueError(f"gsgph_compile_plan failed ({rc})")
+        return prog[: 2 * n.value], off, desc
 
     def build_effects_plan(self, test_crossover: bool):
         """operators_effects.go's single step (XO-only with uniform parents, or self-copy + mutation) as a plan."""

@@ -71,6 +71,19 @@ int gsgph_planner_prefetch(gsgph_planner *pl, int32_t index_best_guess);      /*
 int gsgph_planner_plan(gsgph_planner *pl, const double *fit, int32_t index_best, const gsgp_plan_entry **plan,
                        const int32_t **pool, int32_t *pool_len);
 void gsgph_planner_stats(const gsgph_planner *pl, int64_t *hits, int64_t *misses, int64_t *redrawn_individuals);
+/* Also compile each plan's trees into the interpreter's programs, ahead of time like the draws (worker + n_threads - 1
+ * helper threads; <= 0: default), for gsgp_generation_compiled: the call then starts the kernels at once.  Call before
+ * the first prefetch.  gsgph_planner_programs returns the programs of the plan gsgph_planner_plan returned last
+ * (same lifetime). */
+int gsgph_planner_enable_programs(gsgph_planner *pl, int32_t n_threads);
+int gsgph_planner_programs(const gsgph_planner *pl, const uint32_t **programs, int32_t *n_instructions,
+                           const int32_t **prog_off, const int32_t **prog_desc);
+/* the same staging for hosts that build their plans themselves (a Go host's goroutine): every tree of `plan` through
+ * gsgph_compile_tree's compiler, programs concatenated in slot order (slot = 2*k + which).  programs: 2 uint32 per
+ * instruction, cap instructions (pool_len / 4 + 2 * population_size always suffices); 2: malformed tree, 3: cap */
+int gsgph_compile_plan(const gsgp_plan_entry *plan, int32_t population_size, const int32_t *tree_pool, int32_t pool_len,
+                       int32_t n_symbols, uint32_t *programs, int32_t cap, int32_t *n_instructions, int32_t *prog_off,
+                       int32_t *prog_desc);
 
 /* the one-step experiment of operators_effects.go:1246-1256 as a plan for gsgp_generation: test_crossover != 0 ->
  * every individual is a crossover of two UNIFORMLY drawn parents (random_selection :783-786, :800-806); else every

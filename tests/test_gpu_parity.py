@@ -874,13 +874,13 @@ def test_pipelined_planner_drives_the_same_run_as_build_plan():
     from go_gsgp_b200.host import HostDriver
     X, y, nrow = synth_dataset(3, 1250, 5, nrow=1000)
     runs = []
-    for pipelined in (False, True):
+    for pipelined in (False, True, "programs"):
         h = HostDriver(population_size=100, nvar=5, seed=4)
         sym, trees = h.create_T_F(), h.initialize_population(0)
         e = Engine(population_size=100, nvar=5, nrow=nrow, nrow_test=len(y) - nrow, error_measure=capi.RMSE)
         e.set_dataset(X, y); e.set_constants(sym); e.eval_initial(0, trees)
         fit, fit_test, best = e.fitness_all()
-        pl = h.planner() if pipelined else None
+        pl = h.planner(programs=pipelined == "programs") if pipelined else None
         hist = []
         for g in range(40):
             if pl is None:
@@ -889,7 +889,10 @@ def test_pipelined_planner_drives_the_same_run_as_build_plan():
                 plan, pool = pl.plan(fit, best)
                 pl.prefetch(best)
             hist.append((plan.tobytes(), pool.tobytes()))
-            fit, fit_test, best = e.generation(plan, pool)
+            if pipelined == "programs":                           # trees compiled ahead of time by the planner
+                fit, fit_test, best = e.generation_compiled(plan, pool, *pl.programs())
+            else:
+                fit, fit_test, best = e.generation(plan, pool)
             hist.append((fit.tobytes(), fit_test.tobytes(), best))
         if pl is not None:
             st = pl.stats()
@@ -897,3 +900,47 @@ def test_pipelined_planner_drives_the_same_run_as_build_plan():
         e.close(); h.close()
         runs.append(hist)
     assert runs[0] == runs[1]
+    assert runs[0] == runs[2]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_generation_compiled_checks_its_programs(fused):
+    """gsgp_generation_compiled: programs from gsgph_compile_plan give gsgp_generation's result bit for bit (fused and
+    unfused pipelines); programs that would read outside their tables are refused"""
+    from go_gsgp_b200 import Engine, capi
+    from go_gsgp_b200.host import HostDriver
+    X, y, nrow = synth_dataset(4, 900, 6, nrow=700)
+    os.environ["GSGP_PIPELINE"] = "fused" if fused else "unfused"
+    try:
+        outs = []
+        for compiled in (False, True):
+            h = HostDriver(population_size=64, nvar=6, seed=8, num_constants=3, max_depth_creation=7)
+            sym, trees = h.create_T_F(), h.initialize_population(0)
+            e = Engine(population_size=64, nvar=6, nrow=nrow, nrow_test=len(y) - nrow, num_constants=3, max_depth_creation=7)
+            e.set_dataset(X, y); e.set_constants(sym); e.eval_initial(0, trees)
+            fit, fit_test, best = e.fitness_all()
+            for g in range(6):
+                plan, pool = h.build_plan(fit, best)
+                if compiled:
+                    fit, fit_test, best = e.generation_compiled(plan, pool, *h.compile_plan(plan, pool))
+                else:
+                    fit, fit_test, best = e.generation(plan, pool)
+            outs.append((fit.tobytes(), fit_test.tobytes(), best, e.get_semantics().tobytes()))
+            if compiled:
+                plan, pool = h.build_plan(fit, best)
+                prog, off, desc = h.compile_plan(plan, pool)
+                k = int(np.flatnonzero(desc)[0])
+                for what in ("operand", "range", "level", "opcode"):
+                    p2, o2, d2 = prog.copy(), off.copy(), desc.copy()
+                    if what == "operand": p2[2 * o2[k] + 1] = 0xFFFF0000
+                    if what == "range": o2[k] = len(prog) // 2
+                    if what == "level": p2[2 * o2[k]] |= (5 << 11) | 16
+                    if what == "opcode": p2[2 * o2[k]] |= 7
+                    with pytest.raises(RuntimeError):
+                        e.generation_compiled(plan, pool, p2, o2, d2)
+                fit2 = e.generation_compiled(plan, pool, prog, off, desc)[0]       # the context is still usable
+                assert np.all(np.isfinite(fit2) | np.isnan(fit2))
+            e.close(); h.close()
+        assert outs[0] == outs[1]
+    finally:
+        os.environ.pop("GSGP_PIPELINE", None)

@@ -143,3 +143,38 @@ def test_planner_rejects_a_second_prefetch():
     with pytest.raises(RuntimeError):
         pl.prefetch(0)
     h.close()
+
+
+@pytest.mark.parametrize("kw,p_change,threads", [
+    (dict(population_size=300), 0.5, 3),
+    (dict(population_size=300, num_constants=4, max_depth_creation=8, zero_depth=True), 1.0, 1),
+    (dict(population_size=64), 0.0, 2),
+    (dict(population_size=5, max_depth_creation=10), 0.7, 2),
+])
+def test_planner_programs_equal_compile_plan(kw, p_change, threads):
+    """the programs the planner compiles ahead of time (draft in parallel, repaired runs copied and shifted, redrawn
+    individuals compiled on the spot) are those gsgph_compile_plan builds from the finished plan, slot for slot"""
+    from go_gsgp_b200.host import HostDriver, compile_tree
+    h = HostDriver(nvar=7, seed=21, **kw)
+    pl = h.planner(programs=True, n_threads=threads)
+    P = kw["population_size"]
+    n_sym = 4 + 7 + kw.get("num_constants", 0)
+    for g, (fit, best) in enumerate(_fitness_walk(P, 40, 3, p_change)):
+        plan, pool = pl.plan(fit, best)
+        prog, off, desc = pl.programs()
+        prog_r, off_r, desc_r = h.compile_plan(plan, pool)
+        np.testing.assert_array_equal(desc, desc_r, err_msg=f"generation {g}")
+        np.testing.assert_array_equal(off, off_r)
+        np.testing.assert_array_equal(prog, prog_r)
+        if g == 0:                                              # and gsgph_compile_plan = gsgph_compile_tree per tree
+            for k in range(P):
+                if plan["tree0_len"][k] > 0 and not plan["elite"][k]:
+                    t = pool[plan["tree0_off"][k]: plan["tree0_off"][k] + plan["tree0_len"][k]]
+                    code, ab, need = compile_tree(t, n_sym)
+                    n = desc[2 * k] & 0xFFFFFF
+                    assert n == len(code) and (desc[2 * k] >> 24) == need
+                    np.testing.assert_array_equal(prog[2 * off[2 * k]: 2 * (off[2 * k] + n): 2], code)
+                    np.testing.assert_array_equal(prog[2 * off[2 * k] + 1: 2 * (off[2 * k] + n): 2], ab)
+        if g % 9 != 8:
+            pl.prefetch(best)
+    h.close()

@@ -10,11 +10,11 @@ from bench import synth
 
 P, V, N = int(os.environ.get("POP", 1000)), 20, int(os.environ.get("CASES", 100000))
 X, y = synth(2, N, V); nrow = int(0.8 * N)
-for mode in ("serial", "pipelined"):
+for mode in ("serial", "pipelined", "programs"):
     host = HostDriver(population_size=P, nvar=V, seed=1); sym = host.create_T_F(); trees = host.initialize_population(0)
     e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE)
     e.set_dataset(X, y); e.set_constants(sym); e.eval_initial(0, trees); fit, ft, best = e.fitness_all()
-    pl = host.planner() if mode == "pipelined" else None
+    pl = host.planner(programs=mode == "programs") if mode != "serial" else None
     tb = tg = 0.0
     for i in range(110):
         t0 = time.perf_counter()
@@ -23,7 +23,7 @@ for mode in ("serial", "pipelined"):
         else:
             plan, pool = pl.plan(fit, best); pl.prefetch(best)
         t1 = time.perf_counter()
-        fit, ft, best = e.generation(plan, pool); t2 = time.perf_counter()
+        fit, ft, best = (e.generation_compiled(plan, pool, *pl.programs()) if mode == "programs" else e.generation(plan, pool)); t2 = time.perf_counter()
         if i >= 10: tb += t1 - t0; tg += t2 - t1
     print('%-9s plan %.3f ms  generation() %.3f ms  total %.3f ms/gen  %s' % (mode, tb / 100 * 1e3, tg / 100 * 1e3, (tb + tg) / 100 * 1e3,
           pl.stats() if pl else ''), flush=True)
@@ -31,6 +31,6 @@ for mode in ("serial", "pipelined"):
     for i in range(20):
         plan, pool = (host.build_plan(fit, best) if pl is None else pl.plan(fit, best))
         if pl: pl.prefetch(best)
-        fit, ft, best = e.generation(plan, pool)
+        fit, ft, best = (e.generation_compiled(plan, pool, *pl.programs()) if mode == "programs" else e.generation(plan, pool))
     n, ms, _ = e.profile_read(capi.K_GSOP); print('          gen kernel ms', ms / n, flush=True)
     e.close(); host.close()
