@@ -307,7 +307,9 @@ def main():
     # device computes; winners are picked when the fitness arrives.  Same plans and RNG stream as build_plan.
     # With programs=True the worker threads also compile the trees (gsgp_generation_compiled takes them as they are).
     planner_mode = os.environ.get("GSGP_BENCH_PLANNER", "programs")          # "0": serial gsgph_build_plan, "1": draws only
-    planner = host.planner(programs=planner_mode == "programs") if planner_mode != "0" else None
+    # one process per GPU shares the box's cores: the planner's compile threads scale down with the world size
+    planner_threads = max(1, min(4, (os.cpu_count() or 4) // (4 * world)))
+    planner = host.planner(programs=planner_mode == "programs", n_threads=planner_threads) if planner_mode != "0" else None
     def replay_step(count=False):
         nonlocal fit, best, h2d, d2h
         if planner is not None:
@@ -326,12 +328,21 @@ def main():
                         + ((plan["tree1_len"] - 1) // 4)[plan["tree1_len"] > 0].sum())
             h2d = plan.nbytes + 8 * nodes + 16 * P
             d2h = 16 * P + 4
-    for _ in range(W):
-        replay_step()
+    # the loop itself runs in the compiled host (gsgph_replay_generations: plan -> gsgp_generation_compiled -> fitness
+    # back, K times), like a Go / C++ main would; GSGP_BENCH_E2E_LOOP=python steps it from Python instead
+    compiled_loop = planner is not None and os.environ.get("GSGP_BENCH_E2E_LOOP", "compiled") == "compiled"
+    fit_test = np.zeros_like(fit)
+    def replay(n):
+        nonlocal fit, fit_test, best
+        if compiled_loop:
+            fit, fit_test, best, _, _ = planner.replay_generations(e, n, fit, fit_test, best)
+        else:
+            for _ in range(n):
+                replay_step()
+    replay(W)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        replay_step()
+    replay(K)
     barrier()
     t1 = time.perf_counter()
     replay_step(count=True)
@@ -403,7 +414,7 @@ def main():
                        "store": store, "exchange": exchange,
                        "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / K, "timing": "host wall clock around K gsgp_generation() calls incl. host plan building",
+                    "ms_per_step": ms_e2e / K, "timing": "host wall clock around K generations of the host-replay loop (plan building + gsgp_generation%s with host buffers), loop in %s" % ("_compiled" if planner_mode == "programs" else "", "the compiled host (gsgph_replay_generations)" if compiled_loop else "Python"),
                     "plan_builder": ("pipelined (gsgph_planner_*%s): elite-index guesses right/wrong = %d/%d" %
                                      (", trees compiled ahead: gsgp_generation_compiled" if planner_mode == "programs" else "",
                                       planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)"},

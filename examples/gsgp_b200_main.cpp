@@ -78,14 +78,22 @@ int main(int argc, char **argv)
     };
     write_best();
 
-    std::vector<gsgp_plan_entry> plan((size_t)pop);
-    std::vector<int32_t> trees((size_t)2 * pop * 260);
-    for (int g = 0; g < gens; ++g) {                                            // main GP cycle :1440-1506
-        int32_t tlen = 0;
-        if (gsgph_build_plan(rng, &p, fit.data(), index_best, plan.data(), trees.data(), (int32_t)trees.size(), &tlen)) { fprintf(stderr, "panic: tree pool\n"); return 2; }
-        if (gsgp_generation(ctx, plan.data(), trees.data(), tlen, fit.data(), fit_test.data(), &index_best)) die(ctx, "gsgp_generation");
+    // main GP cycle :1440-1506.  The plan builder is pipelined: while the device computes generation g the planner's
+    // worker threads draw generation g+1's operators / trees / tournament candidates and compile the trees; when the
+    // fitness is back it picks the winners (and repairs a wrong elite guess) -- same plans as gsgph_build_plan.
+    gsgph_planner *planner = gsgph_planner_new(rng, &p);
+    if (!planner || gsgph_planner_enable_programs(planner, 0)) { fprintf(stderr, "panic: planner\n"); return 2; }
+    for (int g = 0; g < gens; ++g) {
+        const gsgp_plan_entry *plan; const int32_t *trees, *prog_off, *prog_desc; const uint32_t *programs;
+        int32_t tlen = 0, n_ins = 0;
+        if (gsgph_planner_plan(planner, fit.data(), index_best, &plan, &trees, &tlen)) { fprintf(stderr, "panic: tree pool\n"); return 2; }
+        gsgph_planner_prefetch(planner, index_best);
+        gsgph_planner_programs(planner, &programs, &n_ins, &prog_off, &prog_desc);
+        if (gsgp_generation_compiled(ctx, plan, trees, tlen, programs, n_ins, prog_off, prog_desc,
+                                     fit.data(), fit_test.data(), &index_best)) die(ctx, "gsgp_generation_compiled");
         write_best();
     }
+    gsgph_planner_free(planner);
     if (gsgph_writer_close(f_train) | gsgph_writer_close(f_test) | gsgph_writer_close(s_train) | gsgph_writer_close(s_test)) {
         fprintf(stderr, "panic: cannot write the output files\n"); return 2;
     }

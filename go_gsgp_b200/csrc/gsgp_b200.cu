@@ -941,10 +941,9 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
             CUC(cudaMalloc((void **)&c->dsem[b], sizeof(double) * (size_t)c->pitch * P));
             CUC(cudaMemsetAsync(c->dsem[b], 0, sizeof(double) * (size_t)c->pitch * P, c->stream));
         }
-        CUC(cudaMalloc((void **)&c->dfit[b], sizeof(double) * P));
-        CUC(cudaMalloc((void **)&c->dfit_test[b], sizeof(double) * P));
-        CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * P, c->stream));
-        CUC(cudaMemsetAsync(c->dfit_test[b], 0, sizeof(double) * P, c->stream));
+        CUC(cudaMalloc((void **)&c->dfit[b], sizeof(double) * 2 * P));           // fit | fit_test: one readback
+        c->dfit_test[b] = c->dfit[b] + P;
+        CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * 2 * P, c->stream));
     }
     CUC(cudaMalloc((void **)&c->dpartial, sizeof(double) * 2 * (size_t)P * std::max(c->n_tiles, c->n_tiles_gen)));
     CUC(cudaMalloc((void **)&c->dsums, sizeof(double) * 2 * P));
@@ -1040,7 +1039,7 @@ void gsgp_destroy(gsgp_ctx *c)
     for (auto &s : c->prof) for (auto &e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(c->dX); cudaFree(c->dy); cudaFree(c->dsym);
     if (c->single_store) c->dsem[1] = nullptr;                        // one allocation
-    for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); cudaFree(c->dfit_test[b]); }
+    for (int b = 0; b < 2; ++b) { cudaFree(c->dsem[b]); cudaFree(c->dfit[b]); }  // dfit_test lives in dfit's allocation
     cudaFree(c->dR); cudaFree(c->dpartial); cudaFree(c->dsums); cudaFree(c->dsums_all);
     cudaFree(c->dsums2); cudaFree(c->dsums_all2); cudaFree(c->dab);
     for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) cudaStreamSynchronize(c->draw_stream[i]);
@@ -1251,8 +1250,9 @@ static int read_fitness(gsgp_ctx *c, double *fit, double *fit_test, int32_t *ind
 {
     const int P = c->cfg.population_size;
     CU(c, c->hfit.reserve(2 * (size_t)P)); CU(c, c->hint.reserve(4));
-    if (fit) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
-    if (fit_test) CU(c, cudaMemcpyAsync(c->hfit.p + P, c->dfit_test[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (fit && fit_test) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * 2 * P, cudaMemcpyDeviceToHost, c->stream));
+    else if (fit) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+    else if (fit_test) CU(c, cudaMemcpyAsync(c->hfit.p + P, c->dfit_test[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
     if (index_best) CU(c, cudaMemcpyAsync(c->hint.p, c->dindex_best, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     c->hint.p[1] = 0;
     if (c->p2p) CU(c, cudaMemcpyAsync(c->hint.p + 1, c->xerr, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -816,6 +816,27 @@ int gsgph_compile_plan(const gsgp_plan_entry *plan, int32_t population_size, con
     return 0;
 }
 
+int gsgph_replay_generations(gsgph_planner *pl, gsgp_ctx *ctx, int32_t n_generations, double *fit, double *fit_test,
+                             int32_t *index_best, double *best_fit_history, double *best_fit_test_history)
+{
+    if (!pl || !ctx || !fit || !fit_test || !index_best || n_generations < 0) return 1;
+    for (int32_t g = 0; g < n_generations; ++g) {
+        const gsgp_plan_entry *plan; const int32_t *pool; int32_t pool_len;
+        if (int rc = gsgph_planner_plan(pl, fit, *index_best, &plan, &pool, &pool_len)) return rc;
+        gsgph_planner_prefetch(pl, *index_best);                                // the next generation's draws start now
+        int rc;
+        if (pl->programs) {
+            const gsgph_planner::Buf &B = pl->buf[pl->out];
+            rc = gsgp_generation_compiled(ctx, plan, pool, pool_len, reinterpret_cast<const uint32_t *>(B.prog.data()), B.n_ins,
+                                          B.prog_off.data(), B.prog_desc.data(), fit, fit_test, index_best);
+        } else rc = gsgp_generation(ctx, plan, pool, pool_len, fit, fit_test, index_best);
+        if (rc) return 4;                                                       // gsgp_last_error(ctx) says why
+        if (best_fit_history) best_fit_history[g] = fit[*index_best];           // :1495-1496
+        if (best_fit_test_history) best_fit_test_history[g] = fit_test[*index_best];
+    }
+    return 0;
+}
+
 void gsgph_planner_stats(const gsgph_planner *pl, int64_t *hits, int64_t *misses, int64_t *redrawn)
 {
     if (hits) *hits = pl ? pl->hits : 0;

@@ -41,6 +41,8 @@ HOST_SIGNATURES = {
                                          C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]),
     "gsgph_compile_plan": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32),
                                      C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gsgph_replay_generations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gsgph_planner_stats": (None, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gsgph_build_effects_plan": (C.c_int, [C.c_void_p, C.POINTER(HostParams), C.c_int32, C.c_void_p,
                                            C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
@@ -207,6 +209,20 @@ class Planner:
         return (self._view(C.addressof(pr.contents), C.c_uint32, 2 * max(n.value, 1), np.uint32)[: 2 * n.value],
                 self._view(C.addressof(off.contents), C.c_int32, 2 * self.P, np.int32),
                 self._view(C.addressof(desc.contents), C.c_int32, 2 * self.P, np.int32))
+
+    def replay_generations(self, engine, n, fit, fit_test, index_best):
+        """gsgph_replay_generations: n generations of the host-replay loop in the compiled host (no Python in between).
+        Returns (fit, fit_test, best, best_fit_history, best_fit_test_history)."""
+        fit, fit_test = np.array(fit, np.float64), np.array(fit_test, np.float64)
+        best = C.c_int32(int(index_best))
+        h0, h1 = np.empty(max(n, 1)), np.empty(max(n, 1))
+        rc = self.L.gsgph_replay_generations(self.h, engine.h, n, capi.dptr(fit), capi.dptr(fit_test), C.byref(best),
+                                             capi.dptr(h0), capi.dptr(h1))
+        if rc == 4:
+            engine._ck(1)
+        if rc:
+            raise RuntimeError(f"gsgph_replay_generations failed ({rc})")
+        return fit, fit_test, best.value, h0[:n], h1[:n]
 
     def prefetch(self, index_best_guess):
         rc = self.L.gsgph_planner_prefetch(self.h, int(index_best_guess))

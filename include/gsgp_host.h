@@ -78,6 +78,14 @@ void gsgph_planner_stats(const gsgph_planner *pl, int64_t *hits, int64_t *misses
 int gsgph_planner_enable_programs(gsgph_planner *pl, int32_t n_threads);
 int gsgph_planner_programs(const gsgph_planner *pl, const uint32_t **programs, int32_t *n_instructions,
                            const int32_t **prog_off, const int32_t **prog_desc);
+/* The generation loop of main_cpu.go:1440-1506 in host-replay mode, n times: plan (pipelined) -> gsgp_generation[_compiled]
+ * -> fitness back.  fit / fit_test / index_best: the current generation's on entry (gsgp_fitness_all or the previous
+ * call), the last generation's on return; *_history (n values each, may be NULL) = fit[best], fit_test[best] per
+ * generation, the fitnesstrain / fitnesstest lines (:1495-1496).  4: a gsgp_* call failed (gsgp_last_error).
+ * On return the following generation's draws are already under way (used by the next call or by gsgph_planner_plan;
+ * gsgph_planner_free returns them to the stream). */
+int gsgph_replay_generations(gsgph_planner *pl, gsgp_ctx *ctx, int32_t n_generations, double *fit, double *fit_test,
+                             int32_t *index_best, double *best_fit_history, double *best_fit_test_history);
 /* the same staging for hosts that build their plans themselves (a Go host's goroutine): every tree of `plan` through
  * gsgph_compile_tree's compiler, programs concatenated in slot order (slot = 2*k + which).  programs: 2 uint32 per
  * instruction, cap instructions (pool_len / 4 + 2 * population_size always suffices); 2: malformed tree, 3: cap */

@@ -944,3 +944,32 @@ def test_generation_compiled_checks_its_programs(fused):
         assert outs[0] == outs[1]
     finally:
         os.environ.pop("GSGP_PIPELINE", None)
+
+
+def test_compiled_replay_loop_equals_stepping_from_python():
+    """gsgph_replay_generations (the host-replay loop in the compiled host) = the same loop stepped from Python"""
+    from go_gsgp_b200 import Engine, capi
+    from go_gsgp_b200.host import HostDriver
+    X, y, nrow = synth_dataset(5, 1250, 5, nrow=1000)
+    outs = []
+    for compiled in (False, True):
+        h = HostDriver(population_size=100, nvar=5, seed=6)
+        sym, trees = h.create_T_F(), h.initialize_population(0)
+        e = Engine(population_size=100, nvar=5, nrow=nrow, nrow_test=len(y) - nrow, error_measure=capi.RMSE)
+        e.set_dataset(X, y); e.set_constants(sym); e.eval_initial(0, trees)
+        fit, fit_test, best = e.fitness_all()
+        pl = h.planner(programs=True)
+        hist = []
+        if compiled:
+            fit, fit_test, best, h0, h1 = pl.replay_generations(e, 12, fit, fit_test, best)
+            fit, fit_test, best, h0b, h1b = pl.replay_generations(e, 13, fit, fit_test, best)
+            hist = list(zip(np.concatenate([h0, h0b]), np.concatenate([h1, h1b])))
+        else:
+            for g in range(25):
+                plan, pool = pl.plan(fit, best)
+                pl.prefetch(best)
+                fit, fit_test, best = e.generation_compiled(plan, pool, *pl.programs())
+                hist.append((fit[best], fit_test[best]))
+        outs.append((hist, fit.tobytes(), fit_test.tobytes(), best, e.generation_index))
+        e.close(); h.close()
+    assert outs[0] == outs[1]
