@@ -142,7 +142,7 @@ struct TreeBuilder {
 // both outcomes take exactly one more draw, so the node is written without branching on the coin.
 inline int32_t grow_tree_array(gsgph_rng *r, const gsgph_params *p, int32_t *t)
 {
-    const int32_t max_depth = p->max_depth_creation, nvar = p->nvar;
+    const int32_t max_depth = p->max_depth_creation, nvar = std::max(p->nvar, 1);   // (no variables: x0, as Intn(0) would panic)
     const bool plain = p->num_constants == 0;
     const int32_t mx = (int32_t)((1u << 31) - 1 - (1u << 31) % (uint32_t)nvar);
     const uint64_t m = (((uint64_t)1 << 63) + (uint64_t)nvar - 1) / (uint64_t)nvar;
@@ -223,7 +223,7 @@ struct PlanWriter {
     PlanWriter(gsgph_rng *r_, const gsgph_params *p_, const double *fit_, int32_t best, gsgp_plan_entry *plan_,
                int32_t *pool_, int32_t cap_, int32_t used_)
         : r(r_), p(p_), fit(fit_), index_best(best), plan(plan_), pool(pool_), cap(cap_), used(used_), tb{r_, p_, {}},
-          tree_max(p_->max_depth_creation < 20 ? ((int64_t)4 << p_->max_depth_creation) : INT32_MAX) {}
+          tree_max(p_->max_depth_creation >= 0 && p_->max_depth_creation < 20 ? ((int64_t)4 << p_->max_depth_creation) : INT32_MAX) {}
     void new_tree(int32_t &off, int32_t &len)
     {
         if (used + tree_max <= cap) {                           // room for any tree: built in place
@@ -650,7 +650,8 @@ struct gsgph_planner {
 
 gsgph_planner *gsgph_planner_new(gsgph_rng *r, const gsgph_params *p)
 {
-    if (!r || !p || p->population_size <= 0 || p->tournament_size <= 0 || p->max_depth_creation < 0 || p->max_depth_creation > 20) return nullptr;
+    if (!r || !p || p->population_size <= 0 || p->tournament_size <= 0 || p->nvar <= 0 || p->num_constants < 0 ||
+        p->max_depth_creation < 0 || p->max_depth_creation > 20) return nullptr;
     gsgph_planner *pl = new gsgph_planner();
     pl->r = r; pl->p = *p;
     const size_t P = (size_t)p->population_size;

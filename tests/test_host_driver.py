@@ -178,3 +178,33 @@ def test_planner_programs_equal_compile_plan(kw, p_change, threads):
         if g % 9 != 8:
             pl.prefetch(best)
     h.close()
+
+
+def test_compile_plan_and_planner_reject_bad_input():
+    import ctypes as C
+    from go_gsgp_b200 import capi
+    from go_gsgp_b200.host import HostDriver, HostParams
+    h = HostDriver(population_size=20, nvar=4, seed=2)
+    fit = np.linspace(1.0, 2.0, 20)
+    plan, pool = h.build_plan(fit, 0)
+    plan, pool = plan.copy(), pool.copy()
+    prog, off, desc = h.compile_plan(plan, pool)
+    assert len(prog) // 2 == int(((plan["tree0_len"] - 1) // 4)[plan["tree0_len"] > 0].sum()
+                                  + ((plan["tree1_len"] - 1) // 4)[plan["tree1_len"] > 0].sum())
+    k = int(np.flatnonzero(plan["tree0_len"] > 0)[0])
+    bad = pool.copy(); bad[plan["tree0_off"][k]] = 99                      # unknown symbol id
+    with pytest.raises(ValueError):
+        h.compile_plan(plan, bad)
+    bad = pool.copy(); bad[plan["tree0_off"][k] + 1] = 0                   # child index does not point forward
+    with pytest.raises(ValueError):
+        h.compile_plan(plan, bad)
+    p2 = plan.copy(); p2["tree0_off"][k] = len(pool)                        # tree outside the pool
+    with pytest.raises(ValueError):
+        h.compile_plan(p2, pool)
+    # planner: bad parameters are refused at creation
+    L = h.L
+    for field, val in (("population_size", 0), ("tournament_size", 0), ("nvar", 0), ("max_depth_creation", 21)):
+        p = HostParams.from_buffer_copy(h.p)
+        setattr(p, field, val)
+        assert not L.gsgph_planner_new(h.rng, C.byref(p)), field
+    h.close()
