@@ -125,3 +125,44 @@ def test_line_writer_reports_unwritable_paths(tmp_path):
     from go_gsgp_b200 import host
     with pytest.raises(OSError):
         host.LineWriter(tmp_path / "no_such_dir" / "x.txt.gz")
+
+
+@pytest.mark.parametrize("threads", [1, 2, 3, 8])
+def test_parse_floats_token_boundaries(threads):
+    """gsgph_parse_floats: a vectorised counting pass decides where each thread's values go, then every thread parses
+    its byte range in place.  Tokens must be counted and parsed once whichever byte a range boundary falls on: random
+    whitespace runs (all six kinds), tokens of every length, no trailing newline, a prefix read (cap), and a malformed
+    token that only matters when it lies within the values asked for."""
+    from go_gsgp_b200.host import _lib
+    L = _lib()
+    rng = np.random.default_rng(100 + threads)
+    vals = rng.normal(size=30_000) * 10.0 ** rng.integers(-30, 30, size=30_000)
+    vals[::97] = np.round(vals[::97])                               # short tokens: "3.0", "-0.0"
+    ws = [" ", "\n", "\t", "\r", "\v", "\f", "  \n", "\t \t", "\r\n"]
+    toks = [("+" if v > 0 and i % 50 == 0 else "") + (repr(float(v)) if i % 4 else f"{v:.17e}") for i, v in enumerate(vals)]
+    text = (ws[3] + "".join(t + ws[int(k)] for t, k in zip(toks, rng.integers(0, len(ws), size=len(toks))))).rstrip() .encode()
+    assert len(text) > (1 << 16)                                    # above the single-thread cut-off
+
+    def parse(buf, cap):
+        out, n = np.full(max(cap, 1), -7.0), C.c_int64()
+        rc = L.gsgph_parse_floats(buf, len(buf), out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n), threads)
+        return rc, n.value, out
+
+    rc, n, out = parse(text, len(vals))
+    assert rc == 0 and n == len(vals)
+    np.testing.assert_array_equal(out.view(np.uint64), vals.view(np.uint64))
+    rc, n, out = parse(text, 1234)                                  # a prefix: the rest is counted, not stored
+    assert rc == 0 and n == len(vals)
+    np.testing.assert_array_equal(out[:1234], vals[:1234])
+    bad = text + b" 1.5abc 2.0"
+    rc, n, _ = parse(bad, len(vals))                                # malformed token beyond the values asked for: ignored
+    assert rc == 0 and n == len(vals) + 2
+    rc, n, _ = parse(bad, len(vals) + 2)
+    assert rc == 2
+    for junk in (b"1e", b"--1", b"0x10", b"1,5", b"."):
+        rc, _, _ = parse(text[: 70_000].rsplit(b" ", 1)[0] + b" " + junk + b" " + text[70_000:], len(vals) + 1)
+        assert rc == 2, junk
+    rc, n, out = parse(b"  \n\t ", 4)
+    assert rc == 0 and n == 0
+    rc, n, out = parse(b"1e999 -1e999 1e-999 inf nan", 5)            # out of range keeps ParseFloat's value
+    assert rc == 0 and n == 5 and out[0] == np.inf and out[1] == -np.inf and out[2] == 0.0 and out[3] == np.inf and np.isnan(out[4])
