@@ -1084,34 +1084,36 @@ inline int format_go_v(double v, char *out)
     if (std::isnan(v)) { memcpy(out, "NaN", 3); return 3; }
     if (std::isinf(v)) { memcpy(out, v > 0 ? "+Inf" : "-Inf", 4); return 4; }
     if (v == 0) { if (std::signbit(v)) { memcpy(out, "-0", 2); return 2; } out[0] = '0'; return 1; }
-    char e[40];
-    const auto r = std::to_chars(e, e + sizeof e, v, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
-    const char *q = e, *endp = r.ptr;
+    // shortest digits in scientific form, written where the result goes: [-]d[.ddd]e[+-]XX[X]; then the decimal point
+    // is moved in place for the exponents Go prints without one
     char *o = out;
-    if (*q == '-') { *o++ = '-'; ++q; }
-    char mant[24]; int nm = 0;
-    for (; q < endp && *q != 'e'; ++q) if (*q != '.') mant[nm++] = *q;
-    int x = 0; bool neg = false;
-    ++q;                                                    // 'e'
-    if (*q == '-') { neg = true; ++q; } else if (*q == '+') ++q;
-    for (; q < endp; ++q) x = x * 10 + (*q - '0');
-    if (neg) x = -x;
-    if (x < -4 || x >= 6) {
-        *o++ = mant[0];
-        if (nm > 1) { *o++ = '.'; memcpy(o, mant + 1, (size_t)nm - 1); o += nm - 1; }
-        *o++ = 'e'; *o++ = x < 0 ? '-' : '+';
-        int ax = x < 0 ? -x : x;
-        if (ax >= 100) { *o++ = (char)('0' + ax / 100); ax %= 100; }
-        *o++ = (char)('0' + ax / 10); *o++ = (char)('0' + ax % 10);
-    } else if (x < 0) {
-        *o++ = '0'; *o++ = '.';
-        for (int i = 0; i < -x - 1; ++i) *o++ = '0';
-        memcpy(o, mant, (size_t)nm); o += nm;
-    } else {
-        for (int i = 0; i <= x; ++i) *o++ = i < nm ? mant[i] : '0';
-        if (nm > x + 1) { *o++ = '.'; memcpy(o, mant + x + 1, (size_t)(nm - x - 1)); o += nm - x - 1; }
+    const auto r = std::to_chars(o, o + 32, v, std::chars_format::scientific);
+    char *endp = r.ptr;
+    if (*o == '-') ++o;                                     // o: first digit
+    char *e = endp - 4;                                     // 'e' sits 4 or 5 chars from the end (2- or 3-digit exponent)
+    if (*e != 'e') --e;
+    int x = e[2] - '0';
+    for (char *q = e + 3; q < endp; ++q) x = x * 10 + (*q - '0');
+    if (e[1] == '-') x = -x;
+    if (x < -4 || x >= 6) return (int)(endp - out);         // exponent form: Go's %v layout is to_chars' own
+    const int nd = (int)(e - o) - (e - o > 1 ? 1 : 0);      // digits (the '.' does not count)
+    if (x >= 0) {                                           // d.ddd -> dddd[.dd] (zero-padded when digits run out)
+        if (nd <= x + 1) {                                  // all digits in front of the point: drop it, pad
+            if (nd > 1) memmove(o + 1, o + 2, (size_t)nd - 1);
+            for (int i = nd; i <= x; ++i) o[i] = '0';
+            return (int)(o + x + 1 - out);
+        }
+        if (x > 0) { memmove(o + 1, o + 2, (size_t)x); o[x + 1] = '.'; }
+        return (int)(o + nd + 1 - out);
     }
-    return (int)(o - out);
+    // 0.000ddd: digits move right by -x + 1 (the point inside them disappears)
+    char d[24];
+    d[0] = o[0];
+    if (nd > 1) memcpy(d + 1, o + 2, (size_t)nd - 1);
+    o[0] = '0'; o[1] = '.';
+    for (int i = 0; i < -x - 1; ++i) o[2 + i] = '0';
+    memcpy(o + 1 - x, d, (size_t)nd);
+    return (int)(o + 1 - x + nd - out);
 }
 }  // namespace
 
@@ -1176,10 +1178,134 @@ struct gsgph_writer {
     static constexpr size_t kBlock = (size_t)4 << 20;  // text bytes per gzip member
     static constexpr size_t kMaxQueued = (size_t)512 << 20;
 
+    // One gzip member holding text[0, n) as ONE dynamic-Huffman deflate block of literals (RFC 1951 3.2.7, RFC 1952).
+    // The output lines are decimal digits with no repeats worth matching: LZ77 at zlib's fastest level finds almost
+    // nothing (ratio 0.49 at 53 MB/s per core) while entropy coding alone gives 0.47 -- so the member is built directly:
+    // byte histogram -> Huffman code lengths -> table-driven bit packing.  Returns false when the code would need
+    // more than 15 bits (the caller falls back to zlib).
+    static bool huffman_member(const char *src, size_t n, std::string &out)
+    {
+        if (n == 0 || n >= ((size_t)1 << 32)) return false;
+        const unsigned char *u = reinterpret_cast<const unsigned char *>(src);
+        // histogram (four tables: consecutive equal bytes do not wait on each other's increments)
+        uint32_t h4[4][256] = {};
+        size_t i = 0;
+        for (; i + 4 <= n; i += 4) { ++h4[0][u[i]]; ++h4[1][u[i + 1]]; ++h4[2][u[i + 2]]; ++h4[3][u[i + 3]]; }
+        for (; i < n; ++i) ++h4[0][u[i]];
+        uint64_t freq[257];
+        for (int c = 0; c < 256; ++c) freq[c] = (uint64_t)h4[0][c] + h4[1][c] + h4[2][c] + h4[3][c];
+        freq[256] = 1;                                                          // end of block
+        // Huffman code lengths: repeatedly merge the two lightest nodes (<= 257 leaves: a linear scan is fine)
+        int parent[2 * 257], nn = 0, live[257], nlive = 0;
+        uint64_t w[2 * 257];
+        int leaf_of[257];
+        for (int c = 0; c < 257; ++c) if (freq[c]) { w[nn] = freq[c]; parent[nn] = -1; leaf_of[c] = nn; live[nlive++] = nn; ++nn; } else leaf_of[c] = -1;
+        uint8_t len[257] = {};
+        if (nlive == 1) return false;                                           // (cannot happen: EOB + >= 1 literal)
+        while (nlive > 1) {
+            int a = 0, b = 1;
+            if (w[live[b]] < w[live[a]]) std::swap(a, b);
+            for (int k = 2; k < nlive; ++k) {
+                if (w[live[k]] < w[live[a]]) { b = a; a = k; }
+                else if (w[live[k]] < w[live[b]]) b = k;
+            }
+            w[nn] = w[live[a]] + w[live[b]]; parent[nn] = -1;
+            parent[live[a]] = nn; parent[live[b]] = nn;
+            const int hi = std::max(a, b), lo = std::min(a, b);
+            live[lo] = nn; live[hi] = live[--nlive];
+            ++nn;
+        }
+        int max_len = 0;
+        for (int c = 0; c < 257; ++c) {
+            if (leaf_of[c] < 0) continue;
+            int d = 0;
+            for (int x = leaf_of[c]; parent[x] >= 0; x = parent[x]) ++d;
+            len[c] = (uint8_t)d;
+            max_len = std::max(max_len, d);
+        }
+        if (max_len > 15) return false;
+        // canonical codes (RFC 1951 3.2.2), stored bit-reversed: deflate packs Huffman codes starting from their MSB
+        auto canonical = [](const uint8_t *l, int count, uint16_t *code) {
+            int bl_count[16] = {}, next[16] = {};
+            for (int c = 0; c < count; ++c) ++bl_count[l[c]];
+            bl_count[0] = 0;
+            for (int b = 1, cd = 0; b < 16; ++b) { cd = (cd + bl_count[b - 1]) << 1; next[b] = cd; }
+            for (int c = 0; c < count; ++c) {
+                if (!l[c]) { code[c] = 0; continue; }
+                int v = next[l[c]]++, r = 0;
+                for (int b = 0; b < l[c]; ++b) { r = (r << 1) | (v & 1); v >>= 1; }
+                code[c] = (uint16_t)r;
+            }
+        };
+        uint16_t code[257];
+        canonical(len, 257, code);
+        // the 257 + 2 code lengths, run-length coded with symbols 16 / 17 / 18 (3.2.7); the two distance codes have
+        // length 1 (what zlib sends when no distance is used)
+        uint8_t all[259];
+        memcpy(all, len, 257); all[257] = 1; all[258] = 1;
+        struct Sym { uint8_t s, extra, nbits; };
+        std::vector<Sym> rle;
+        for (int k = 0; k < 259;) {
+            int run = 1;
+            while (k + run < 259 && all[k + run] == all[k]) ++run;
+            const uint8_t v = all[k];
+            int left = run;
+            if (v == 0) {
+                while (left >= 11) { const int r = std::min(left, 138); rle.push_back({18, (uint8_t)(r - 11), 7}); left -= r; }
+                if (left >= 3) { rle.push_back({17, (uint8_t)(left - 3), 3}); left = 0; }
+                while (left-- > 0) rle.push_back({0, 0, 0});
+            } else {
+                rle.push_back({v, 0, 0}); --left;
+                while (left >= 3) { const int r = std::min(left, 6); rle.push_back({16, (uint8_t)(r - 3), 2}); left -= r; }
+                while (left-- > 0) rle.push_back({v, 0, 0});
+            }
+            k += run;
+        }
+        // a fixed complete code for the 19 code-length symbols: the 13 that can occur often get 4 bits, 6 get 5 bits
+        uint8_t cl_len[19];
+        for (int c = 0; c < 19; ++c) cl_len[c] = 5;
+        for (int c : {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 18}) cl_len[c] = 4;
+        uint16_t cl_code[19];
+        canonical(cl_len, 19, cl_code);
+        // worst case: every literal 15 bits
+        out.resize(10 + 8 + 400 + (n * 15 + 7) / 8 + 16);
+        unsigned char *o = reinterpret_cast<unsigned char *>(&out[0]);
+        static const unsigned char head[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
+        memcpy(o, head, 10); o += 10;
+        uint64_t acc = 0; int nb = 0;
+        auto put = [&](uint32_t v, int bits) {                                  // LSB-first bit stream
+            acc |= (uint64_t)v << nb; nb += bits;
+            if (nb >= 32) { memcpy(o, &acc, 4); o += 4; acc >>= 32; nb -= 32; }
+        };
+        put(1, 1); put(2, 2);                                                   // BFINAL = 1, BTYPE = 10 (dynamic)
+        put(0, 5); put(1, 5); put(19 - 4, 4);                                   // HLIT = 257, HDIST = 2, HCLEN = 19
+        static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        for (int k = 0; k < 19; ++k) put(cl_len[order[k]], 3);
+        for (const Sym &y : rle) { put(cl_code[y.s], cl_len[y.s]); if (y.nbits) put(y.extra, y.nbits); }
+        // the literals: code | length << 16 per byte, two symbols per flush check (2 x 15 bits on top of < 32)
+        uint32_t tab[256];
+        for (int c = 0; c < 256; ++c) tab[c] = (uint32_t)code[c] | ((uint32_t)len[c] << 16);
+        i = 0;
+        for (; i + 2 <= n; i += 2) {
+            const uint32_t t0 = tab[u[i]], t1 = tab[u[i + 1]];
+            acc |= (uint64_t)(t0 & 0xFFFFu) << nb; nb += (int)(t0 >> 16);
+            acc |= (uint64_t)(t1 & 0xFFFFu) << nb; nb += (int)(t1 >> 16);
+            if (nb >= 32) { memcpy(o, &acc, 4); o += 4; acc >>= 32; nb -= 32; }
+        }
+        for (; i < n; ++i) put(code[u[i]], len[u[i]]);
+        put(code[256], len[256]);                                               // end of block
+        while (nb > 0) { *o++ = (unsigned char)(acc & 0xFF); acc >>= 8; nb -= 8; }
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), u, (uInt)n), isize = (uint32_t)n;
+        memcpy(o, &crc, 4); memcpy(o + 4, &isize, 4); o += 8;                   // little-endian host (x86-64)
+        out.resize((size_t)(o - reinterpret_cast<unsigned char *>(&out[0])));
+        return true;
+    }
     static bool deflate_member(const char *src, size_t n, std::string &out)
     {
+        static const bool use_zlib = getenv("GSGP_GZIP_ZLIB") != nullptr;       // A/B: zlib's own encoder for everything
+        if (!use_zlib && huffman_member(src, n, out)) return true;
         z_stream zs{};
-        if (deflateInit2(&zs, Z_BEST_SPEED, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        if (deflateInit2(&zs, Z_BEST_SPEED, Z_DEFLATED, 15 + 16, 8, Z_HUFFMAN_ONLY) != Z_OK) return false;
         out.resize(deflateBound(&zs, (uLong)n) + 64);
         zs.next_in = reinterpret_cast<Bytef *>(const_cast<char *>(src)); zs.avail_in = (uInt)n;
         zs.next_out = reinterpret_cast<Bytef *>(&out[0]); zs.avail_out = (uInt)out.size();
@@ -1247,6 +1373,21 @@ struct gsgph_writer {
         flush_pending(true);
     }
 };
+
+int gsgph_gzip_member(const char *src, int64_t n, char *out, int64_t cap, int64_t *len_out)
+{
+    if (!src || n < 0 || !out) return 1;
+    std::string m;
+    if (n == 0 || !gsgph_writer::deflate_member(src, (size_t)n, m)) {
+        if (n != 0) return 2;
+        static const unsigned char empty[20] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        m.assign(reinterpret_cast<const char *>(empty), sizeof empty);
+    }
+    if (len_out) *len_out = (int64_t)m.size();
+    if ((int64_t)m.size() > cap) return 3;
+    memcpy(out, m.data(), m.size());
+    return 0;
+}
 
 gsgph_writer *gsgph_writer_open(const char *path, int32_t n_threads)
 {

@@ -59,6 +59,7 @@ HOST_SIGNATURES = {
     "gsgph_writer_semantic": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int64]),
     "gsgph_writer_float": (C.c_int, [C.c_void_p, C.c_double]),
     "gsgph_writer_close": (C.c_int, [C.c_void_p]),
+    "gsgph_gzip_member": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
 _bound = False
@@ -127,6 +128,16 @@ def compile_tree(tree, n_symbols):
     if rc:
         raise ValueError(f"malformed tree (gsgph_compile_tree rc={rc})")
     return out[0:2 * n.value:2].copy(), out[1:2 * n.value:2].copy(), need.value
+
+
+def gzip_member(data: bytes) -> bytes:
+    """gsgph_gzip_member: data as one gzip member, the ".gz" writers' compressor"""
+    cap = len(data) * 2 + 1024
+    buf, n = C.create_string_buffer(cap), C.c_int64()
+    rc = _lib().gsgph_gzip_member(data, len(data), buf, cap, C.byref(n))
+    if rc:
+        raise RuntimeError(f"gsgph_gzip_member failed ({rc})")
+    return buf.raw[: n.value]
 
 
 class LineWriter:

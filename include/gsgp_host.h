@@ -134,6 +134,11 @@ gsgph_writer *gsgph_writer_open(const char *path, int32_t n_threads);          /
 int gsgph_writer_semantic(gsgph_writer *w, const double *v, int64_t n);        /* fmt.Fprintln(file, Semantic) :1499-1500 */
 int gsgph_writer_float(gsgph_writer *w, double v);                            /* fmt.Fprintln(file, fit[best]) :1495-1496 */
 int gsgph_writer_close(gsgph_writer *w);
+/* the writers' compressor on its own: src[0, n) as one gzip member (what a ".gz" writer emits per 4 MB of text).  The
+ * lines are decimal digits -- nothing for LZ77 to match -- so the member is one dynamic-Huffman block of literals built
+ * directly (histogram, code lengths, table-driven bit packing), with zlib's Z_HUFFMAN_ONLY as the fallback for input
+ * whose code would exceed 15 bits.  cap >= n + n/8 + 512 always suffices; 3: cap too small (len_out = needed). */
+int gsgph_gzip_member(const char *src, int64_t n, char *out, int64_t cap, int64_t *len_out);
 
 #ifdef __cplusplus
 }

@@ -166,3 +166,23 @@ def test_parse_floats_token_boundaries(threads):
     assert rc == 0 and n == 0
     rc, n, out = parse(b"1e999 -1e999 1e-999 inf nan", 5)            # out of range keeps ParseFloat's value
     assert rc == 0 and n == 5 and out[0] == np.inf and out[1] == -np.inf and out[2] == 0.0 and out[3] == np.inf and np.isnan(out[4])
+
+
+def test_gzip_member_round_trips_any_bytes():
+    """gsgph_gzip_member (one dynamic-Huffman block of literals, built directly; zlib's Z_HUFFMAN_ONLY when a code would
+    exceed 15 bits): whatever the bytes, gzip reads the member back, members concatenate, and digit text comes out at
+    the entropy-coding ratio."""
+    import gzip
+    from go_gsgp_b200.host import gzip_member, format_semantic
+    rng = np.random.default_rng(12)
+    text = (format_semantic(rng.normal(size=200_000)) + "\n").encode()
+    fib = b"".join(bytes([i]) * f for i, f in enumerate([1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584,
+                                                          4181, 6765, 10946, 17711, 28657, 46368, 75025]))   # depth 24 > 15: fallback
+    cases = [text, b"", b"7", b"aaaaaaaaaaaaaaaaaaaaaaaa", bytes(range(256)) * 5, rng.integers(0, 256, 100_000, dtype=np.uint8).tobytes(),
+             b"0123456789" * 1000 + b"\x00", fib, text[:3], text[:4], text[:5]]
+    members = [gzip_member(c) for c in cases]
+    for c, m in zip(cases, members):
+        assert m[:3] == b"\x1f\x8b\x08"
+        assert gzip.decompress(m) == c
+    assert gzip.decompress(b"".join(members)) == b"".join(cases)              # a multi-member file reads as one stream
+    assert len(members[0]) < 0.48 * len(text)
