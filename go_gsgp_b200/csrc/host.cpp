@@ -295,16 +295,29 @@ struct PlanWriter {
 
 extern "C" {
 
-gsgph_rng *gsgph_rng_new(int64_t seed)
+gsgph_rng *gsgph_rng_new(int64_t seed)                         // rngSource.Seed: Go's own stream for this seed
 {
+    static const uint64_t cooked[607] = {
+#include "go_rng_cooked.inc.h"
+    };
+    auto seedrand = [](int32_t x) {                             // x[n+1] = 48271 * x[n] mod (2^31 - 1)
+        const int32_t hi = x / 44488, lo = x % 44488;
+        x = 48271 * lo - 3399 * hi;
+        return x < 0 ? x + 2147483647 : x;
+    };
     gsgph_rng *r = new gsgph_rng();
     uint64_t vec[607];
-    uint64_t x = (uint64_t)seed;
-    for (int i = 0; i < 607; ++i) {
-        uint64_t z = (x += 0x9E3779B97F4A7C15ull);
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        vec[i] = z ^ (z >> 31);
+    seed %= 2147483647;
+    if (seed < 0) seed += 2147483647;
+    if (seed == 0) seed = 89482311;
+    int32_t x = (int32_t)seed;
+    for (int i = -20; i < 607; ++i) {
+        x = seedrand(x);
+        if (i < 0) continue;
+        uint64_t u = (uint64_t)x << 40;
+        x = seedrand(x); u ^= (uint64_t)x << 20;
+        x = seedrand(x); u ^= (uint64_t)x;
+        vec[i] = u ^ cooked[i];
     }
     r->seed_from_go_layout(vec);
     return r;

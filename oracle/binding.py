@@ -82,7 +82,7 @@ def build(force: bool = False) -> str:
     """Compile the oracle with the committed recipe (oracle/Makefile)."""
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("gsgp_oracle.c", "gsgp_oracle.h", "oracle_cli.c", "Makefile")
+        for f in ("gsgp_oracle.c", "gsgp_oracle.h", "oracle_cli.c", "go_rng_cooked.inc.h", "Makefile")
         if os.path.exists(os.path.join(_HERE, f))
     ):
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])

@@ -36,23 +36,42 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static uint64_t splitmix64(uint64_t *x)
+/* Go math/rand (v1) seed table (math/rand/rng.go: rngCooked).  Go's stdlib is not in /root/reference and Go is not
+ * installed; the table is recomputed from its definition by tools/gen_go_rng_cooked.py and pinned by known outputs of
+ * Go programs (tests/test_oracle_kat.py::test_go_math_rand_known_answers). */
+static const uint64_t go_rng_cooked[607] = {
+#include "go_rng_cooked.inc.h"
+};
+
+static int32_t go_seedrand(int32_t x)           /* x[n+1] = 48271 * x[n] mod (2^31 - 1) */
 {
-    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+    int32_t hi = x / 44488, lo = x % 44488;
+    x = 48271 * lo - 3399 * hi;
+    return x < 0 ? x + 2147483647 : x;
 }
 
-/* Go math/rand rngSource.Seed shape: vec[607], tap=0, feed=607-273.
- * rngCooked is unavailable offline, so vec[] is filled by splitmix64(seed). */
+/* ORC_RNG_ALFG: Go's rngSource.Seed (what rand.Seed(cfg.rng_seed), main_cpu.go:1367, runs): vec[607], tap = 0,
+ * feed = 607 - 273; the stream is bit-identical to Go's. */
 void orc_rng_seed(orc_rng *r, int kind, int64_t seed)
 {
     memset(r, 0, sizeof *r);
     r->kind = kind;
     if (kind == ORC_RNG_ALFG) {
-        uint64_t x = (uint64_t)seed;
-        for (int i = 0; i < 607; ++i) r->vec[i] = splitmix64(&x);
+        seed %= 2147483647;
+        if (seed < 0) seed += 2147483647;
+        if (seed == 0) seed = 89482311;
+        int32_t x = (int32_t)seed;
+        for (int i = -20; i < 607; ++i) {
+            x = go_seedrand(x);
+            if (i >= 0) {
+                uint64_t u = (uint64_t)x << 40;
+                x = go_seedrand(x);
+                u ^= (uint64_t)x << 20;
+                x = go_seedrand(x);
+                u ^= (uint64_t)x;
+                r->vec[i] = u ^ go_rng_cooked[i];
+            }
+        }
         r->tap = 0;
         r->feed = 607 - 273;
     } else {

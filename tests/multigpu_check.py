@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import binding as ob                      # noqa: E402
 from go_gsgp_b200 import Engine, capi                 # noqa: E402
-from tests.util import synth_dataset, rel_err         # noqa: E402
+from tests.util import synth_dataset, rel_err, same_best         # noqa: E402
 
 
 def main():
@@ -50,7 +50,7 @@ def main():
         e.eval_initial(0, [o.initial_tree(i) for i in range(P)])
         o.evaluate()
         fit, fit_test, best = e.fitness_all()
-        assert best == o.index_best and np.all(rel_err(fit, o.fit()) <= 1e-9)
+        assert same_best(best, o) and np.all(rel_err(fit, o.fit()) <= 1e-9)
         tr_lo, tr_hi = Engine.shard_range(nrow, rank, world)
         te_lo, te_hi = Engine.shard_range(N - nrow, rank, world)
         for g in range(6):
@@ -65,7 +65,7 @@ def main():
                 for f in ("op", "elite", "p1", "p2"):
                     live = ref["elite"] == 0 if f in ("p1", "p2") else slice(None)
                     assert np.array_equal(plan[f][live], ref[f][live]), (rank, g, f)
-            assert best == o.index_best, (rank, g, best, o.index_best)
+            assert same_best(best, o), (rank, g, best, o.index_best)
             assert np.all(rel_err(fit, o.fit()) <= 1e-9) and np.all(rel_err(fit_test, o.fit_test()) <= 1e-9)
             allfit = [torch.zeros(P, dtype=torch.float64, device="cuda") for _ in range(world)]
             dist.all_gather(allfit, torch.from_numpy(fit).cuda())

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import binding as ob
-from tests.util import synth_dataset, toy_fixture, rel_err
+from tests.util import synth_dataset, toy_fixture, rel_err, same_best
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -190,7 +190,7 @@ def test_fused_path_runs_long_programs_in_chunks(depth, full):
     fit, fit_test, best = e.generation(plan, pool)
     assert_close(e.get_semantics(), o.semantics(), TOL, "children of long programs")
     assert_close(fit, o.fit(), TOL, "fit"); assert_close(fit_test, o.fit_test(), TOL, "fit_test")
-    assert best == o.index_best
+    assert same_best(best, o)
     for t in trees[:4]:                                                # and the trees alone, bit for bit (unfused interpreter)
         np.testing.assert_array_equal(e.eval_trees([t])[0], o.semantic_evaluate_array(t))
     e.close(); o.close()
@@ -202,7 +202,7 @@ def test_initial_evaluate(measure):
     o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=100, error_measure=measure)
     assert_close(fit, o.fit(), 1e-12, "fit")
     assert_close(fit_test, o.fit_test(), 1e-12, "fit_test")
-    assert best == o.index_best
+    assert same_best(best, o)
     for i in (0, 17, 99):
         np.testing.assert_array_equal(e.get_semantic(i), o.semantic(i))
     e.close()
@@ -215,7 +215,7 @@ def _lockstep_replay(o, e, gens, tol=TOL, check_sem_every=1):
         fit, fit_test, best = e.generation(plan, pool)
         assert_close(fit, o.fit(), tol, f"gen {g} fit")
         assert_close(fit_test, o.fit_test(), tol, f"gen {g} fit_test")
-        assert best == o.index_best, f"gen {g} best"
+        assert same_best(best, o), f"gen {g} best"
         if g % check_sem_every == 0:
             for i in range(0, o.P, max(1, o.P // 16)):
                 assert_close(e.get_semantic(i), o.semantic(i), tol, f"gen {g} sem[{i}]")
@@ -273,7 +273,7 @@ def test_semantic_feeding_seeds():
     seeds = [y + rng.normal(0, 0.05 + 0.001 * k, size=900) for k in range(8)]
     o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=24, seeds=seeds, seed=2)
     assert_close(fit, o.fit(), 1e-12, "seeded fit")
-    assert best == o.index_best and best < 8
+    assert same_best(best, o) and best < 8
     _lockstep_replay(o, e, 8)
     e.close()
 
@@ -324,7 +324,7 @@ def test_sigmoid_quirks_through_crossover_and_mutation():
     for k in range(7):
         np.testing.assert_array_equal(got[k], want[k])
     assert_close(fit, o.fit(), TOL, "quirk fit")
-    assert best == o.index_best
+    assert same_best(best, o)
     e.close()
 
 
@@ -574,14 +574,14 @@ def test_wide_dataset_falls_back_to_the_unfused_pipeline():
     X, y, nrow = synth_dataset(5, 2000, 120)
     for rng_kind in (ob.RNG_ALFG, ob.RNG_PHILOX):
         o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=40, seed=2, rng_kind=rng_kind, num_random_constants=2)
-        assert best == o.index_best
+        assert same_best(best, o)
         for _ in range(4):
             o.generation()
             if rng_kind == ob.RNG_PHILOX:
                 e.run_generations(1); fit, fit_test, best = e.get_fitness()
             else:
                 fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
-            assert best == o.index_best
+            assert same_best(best, o)
             assert_close(fit, o.fit(), TOL, "fit"); assert_close(fit_test, o.fit_test(), TOL, "fit_test")
         assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
         e.close(); o.close()
@@ -599,11 +599,11 @@ def test_edge_shapes_lockstep(kw):
     args = dict(population_size=24, seed=4)
     args.update(kw)
     o, e, (fit, fit_test, best) = _mk(X, y, nrow, **args)
-    assert best == o.index_best
+    assert same_best(best, o)
     for _ in range(4):
         o.generation()
         fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
-        assert best == o.index_best
+        assert same_best(best, o)
         assert_close(fit, o.fit(), TOL, "fit")
         assert_close(fit_test, o.fit_test(), TOL, "fit_test")
     assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")
@@ -623,7 +623,7 @@ def test_linear_scaling_lockstep(kw):
     kw = dict(kw)
     device = kw.get("rng_kind") == ob.RNG_PHILOX
     o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=60, seed=8, use_linear_scaling=1, **kw)
-    assert best == o.index_best
+    assert same_best(best, o)
     assert_close(fit, o.fit(), TOL, "initial fit (ls)")
     assert_close(fit_test, o.fit_test(), TOL, "initial fit_test (ls)")
     for _ in range(5):
@@ -633,7 +633,7 @@ def test_linear_scaling_lockstep(kw):
             fit, fit_test, best = e.get_fitness()
         else:
             fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
-        assert best == o.index_best
+        assert same_best(best, o)
         assert_close(fit, o.fit(), TOL, "fit (ls)")
         assert_close(fit_test, o.fit_test(), TOL, "fit_test (ls)")
     assert_close(e.get_semantics(), o.semantics(), TOL, "semantics")

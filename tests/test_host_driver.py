@@ -50,6 +50,28 @@ def test_host_plan_equals_oracle_plan(kw):
         np.testing.assert_array_equal(pool[: len(o.last_tree_pool())], o.last_tree_pool())
 
 
+def test_host_rng_is_gos_seeded_stream():
+    """gsgph_rng_new(seed) is rand.Seed(seed) (main_cpu.go:1367): known outputs of Go programs, and the oracle's stream
+    draw for draw across refills of the 607-word window with mixed Float64 / Intn calls."""
+    from go_gsgp_b200 import host
+    L = host._lib()
+    r = L.gsgph_rng_new(1)
+    assert [L.gsgph_rng_intn(r, 100) for _ in range(10)] == [81, 87, 47, 59, 81, 18, 25, 40, 56, 0]
+    L.gsgph_rng_free(r)
+    r = L.gsgph_rng_new(1)
+    assert [L.gsgph_rng_float64(r) for _ in range(3)] == [0.6046602879796196, 0.9405090880450124, 0.6645600532184904]
+    L.gsgph_rng_free(r)
+    for seed in (42, 0, -5, 2**31 - 1, 2**40 + 17):
+        r, o = L.gsgph_rng_new(seed), ob.Rng(ob.RNG_ALFG, seed)
+        for i in range(4000):
+            if i % 3 == 0:
+                assert L.gsgph_rng_float64(r) == o.float64()
+            else:
+                n = (2, 4, 20, 1000, 100, 7)[i % 6]
+                assert L.gsgph_rng_intn(r, n) == o.intn(n)
+        L.gsgph_rng_free(r)
+
+
 def test_format_float_matches_go_v():
     from go_gsgp_b200.host import format_float as f
     rng = np.random.default_rng(0)
@@ -118,7 +140,8 @@ def test_pipelined_planner_equals_build_plan(kw, p_change):
         plan_a, pool_a = a.build_plan(fit, best)
         plan_b, pool_b = pl.plan(fit, best)
         assert plan_a.tobytes() == plan_b.tobytes(), f"generation {g}"
-        np.testing.assert_array_equal(pool_a, pool_b)
+        if (plan_a["tree0_off"] >= 0).any():                    # (a generation without trees returns one unused slot)
+            np.testing.assert_array_equal(pool_a, pool_b)
         if g % 9 != 8 and g != 59:                              # now and then no prefetch: the serial path
             pl.prefetch(best)
     st = pl.stats()

@@ -6,6 +6,8 @@ the oracle's only anchor ("parity unpinned").
 """
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -50,6 +52,48 @@ def test_rng_derivations():
         assert min(xs) == 0 and max(xs) == 12
         fs = [r.float64() for _ in range(2000)]
         assert 0.0 <= min(fs) and max(fs) < 1.0 and 0.45 < sum(fs) / len(fs) < 0.55
+
+
+def _go_rng_tool():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_go_rng_cooked", os.path.join(root, "tools", "gen_go_rng_cooked.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    return gen
+
+
+def test_go_math_rand_known_answers():
+    """ORC_RNG_ALFG is Go's math/rand (v1) seeded source, bit for bit: outputs of real Go programs with rand.Seed(1)
+    (what main_cpu.go:1367 runs with the default -seed) -- the Int63 / Intn(100) / Float64 sequences every Go program
+    that never seeds prints -- and with seed 42.  These pin the RNG half of the oracle to the real reference."""
+    gen = _go_rng_tool()
+    m63 = 2**63 - 1
+    r = ob.Rng(ob.RNG_ALFG, 1)
+    assert [r.uint64() & m63 for _ in range(10)] == gen.KAT_INT63_SEED1
+    r = ob.Rng(ob.RNG_ALFG, 1)
+    assert [r.intn(100) for _ in range(10)] == gen.KAT_INTN100_SEED1
+    r = ob.Rng(ob.RNG_ALFG, 1)
+    assert [r.float64() for _ in range(10)] == gen.KAT_FLOAT64_SEED1
+    r = ob.Rng(ob.RNG_ALFG, 42)
+    assert [r.intn(100) for _ in range(2)] == gen.KAT_INTN100_SEED42
+    # Seed's reductions: seed mod (2^31 - 1), negatives shifted up, 0 -> 89482311
+    for s, same_as in ((2**31 - 1 + 1, 1), (-(2**31 - 1) + 1, 1), (0, 89482311), (2**31 - 1, 89482311)):
+        a, b = ob.Rng(ob.RNG_ALFG, s), ob.Rng(ob.RNG_ALFG, same_as)
+        assert [a.uint64() for _ in range(5)] == [b.uint64() for _ in range(5)]
+    # and against the tool's pure-Python restatement over a long stretch (past several refills of the 607 window)
+    g = gen.GoSource(20261019, gen.cooked_table(check=False))
+    r = ob.Rng(ob.RNG_ALFG, 20261019)
+    assert [r.uint64() for _ in range(3000)] == [g.uint64() for _ in range(3000)]
+
+
+def test_generated_go_seed_table_is_current():
+    """oracle/go_rng_cooked.inc.h and go_gsgp_b200/csrc/go_rng_cooked.inc.h are generated: both must be what
+    tools/gen_go_rng_cooked.py computes (7.8e12 generator steps by jump-ahead, known answers asserted)."""
+    gen = _go_rng_tool()
+    text = gen.render(check=True)
+    for path in gen.targets():
+        assert open(path).read() == text, path
 
 
 def test_alfg_is_seed_deterministic():

@@ -31,3 +31,12 @@ def rel_err(a, b):
     e = np.where(both_nan | same_inf, 0.0, e)
     e = np.where(np.isnan(e), np.inf, e)
     return e
+
+
+def same_best(best, o, tol=1e-11):
+    """The CUDA path's best index against the oracle's: equal, or the two candidates' fitness ties to within the
+    summation-order noise in the oracle's own values (decisions are exact given equal fitness values)."""
+    if best == o.index_best:
+        return True
+    f = o.fit()
+    return bool(rel_err(f[best], f[o.index_best]) <= tol)
