@@ -100,7 +100,12 @@ def test_datasets_full_of_zeros_and_extremes_stay_bit_exact(fused):
                     plan[k] = (ob.OP_MUT, 0, 1, 0, off[2 * k], len(batch[2 * k]), off[2 * k + 1], len(batch[2 * k + 1]), 1.0)
             o.generation_replay(plan, pool)
             e.generation(plan, pool)
-            assert_close(e.get_semantics(), o.semantics(), 1e-12, f"children of trees {g0}..")
+            # (absolute floor: sigma(R1) - sigma(R2) cancels when R1 ~ R2, leaving sigma's own rounding, <= 3e-16 each)
+            got, want = e.get_semantics(), o.semantics()
+            err = rel_err(got, want)
+            with np.errstate(invalid="ignore"):
+                bad = (err > 1e-12) & ~(np.abs(got - want) <= 1e-15)
+            assert not bad.any(), f"children of trees {g0}..: max rel err {np.max(err[bad]):.3e} at {np.flatnonzero(bad)[:4]}"
             for i, sem in enumerate(seeds):                    # same parents for the next batch
                 o.seed_semantic(i, sem); e.seed_semantic(i, sem)
             o.evaluate(); e.fitness_all()
