@@ -2,8 +2,8 @@
 // include/gsgp_b200.h + include/gsgp_host.h, i.e. what main_b200.go does from Go.  It is an ABI
 // example and link test, not the reference's CLI: a handful of positional options, the reference's file formats in
 // (read_input_data :381-421, read_sem :710-733) and out (best-of-generation fitness / semantic lines :1404-1413,
-// :1494-1505).  The RNG is the library's math/rand stand-in (gsgp_host.h), so runs are reproducible but do not
-// replay Go's stream.
+// :1494-1505).  The RNG is the library's restatement of math/rand (gsgp_host.h): Go's own stream for the seed, so the
+// draws are the ones main_cpu.go makes with the same -seed.
 //
 //   gsgp_b200_main <train> <test> <out_dir> [generations=10] [population=200] [seed=1] [linsc=0] [seed files...]
 #include <cstdio>

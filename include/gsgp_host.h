@@ -19,9 +19,12 @@ extern "C" {
 
 typedef struct gsgph_rng gsgph_rng;
 
-/* math/rand stand-in: Go's additive lagged Fibonacci source (607,273) and Go's derivations of
- * Float64/Intn.  Go's 607-entry seed table is not available offline, so the
- * state is filled by splitmix64(seed): streams are reproducible, not equal to Go's. */
+/* math/rand (v1) restated: Go's additive lagged Fibonacci source (607,273), seeded as rand.Seed(seed) does, and Go's
+ * derivations of Float64/Intn.  The stream is Go's own, bit for bit: the 607-word seed table of
+ * the Go stdlib is recomputed from its definition by tools/gen_go_rng_cooked.py (csrc/go_rng_cooked.inc.h) and pinned
+ * by known outputs of Go programs (rand.Seed(1): Intn(100) = 81 87 47 59 81 ..., Float64 = 0.6046602879796196 ...;
+ * tests/test_host_driver.py::test_host_rng_is_gos_seeded_stream).  A C++ host over this library therefore makes the
+ * draws main_cpu.go makes for the same -seed. */
 gsgph_rng *gsgph_rng_new(int64_t seed);                    /* rand.Seed   main_cpu.go:1367 */
 void       gsgph_rng_free(gsgph_rng *r);
 double     gsgph_rng_float64(gsgph_rng *r);

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs; the product package (go_gsgp_b200) never imports this.
-PARITY UNPINNED by the reference's own tests (see gsgp_oracle.h).
+PARITY UNPINNED by the reference's own tests (see gsgp_oracle.h); the random stream is Go's own, pinned by known
+outputs of Go programs.
 """
 from __future__ import annotations
 

@@ -2,7 +2,8 @@
  * gsgp_oracle.c -- CPU ORACLE (test infrastructure, see gsgp_oracle.h).
  *
  * Plain-C restatement of akiross/go-gsgp main_cpu.go's generation-loop path.  PARITY UNPINNED by
- * the reference's own tests (it ships none for this path); pinned by hand-derived KATs only.
+ * the reference's own tests (it ships none for this path); pinned by hand-derived KATs and, for the
+ * random stream, by known outputs of real Go programs (gsgp_oracle.h).
  * Build with -ffp-contract=off: Go on amd64 never fuses a*b+c, and neither may this file.
  */
 #define _GNU_SOURCE

@@ -8,9 +8,10 @@
  *
  * PARITY UNPINNED: the reference ships no golden vectors, fixtures or runnable tests for this
  * path (main_test.go does not compile at the reference snapshot) and there is no Go toolchain in
- * this image, so the reference itself cannot be run.  The oracle is pinned only by hand-derived
- * known-answer tests (tests/test_oracle_kat.py) and by the 4-row toy
- * dataset of main_test.go:107-112.
+ * this image, so the reference itself cannot be run.  The oracle is pinned by hand-derived
+ * known-answer tests (tests/test_oracle_kat.py), by the 4-row toy
+ * dataset of main_test.go:107-112 and -- for the random stream, i.e. every draw the reference makes
+ * after rand.Seed (main_cpu.go:1367) -- by known outputs of real Go programs (below).
  *
  * Every function cites the reference file:line it restates.
  */
@@ -25,12 +26,16 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------ RNG ------------------ */
-/* The reference draws everything from Go's global math/rand stream (main_cpu.go:1367).  That
- * generator's 607-entry seed table (rngCooked) is not in /root/reference and Go is not installed,
- * so the uint64 SOURCE is injectable; the derived draws (Int63, Int31, Float64, Intn) restate Go's
- * math/rand v1 derivations on top of whichever source is plugged in.
- *   ORC_RNG_ALFG    sequential additive lagged-Fibonacci (607,273) like Go's rngSource, seeded with
- *                   splitmix64 instead of rngCooked (stand-in for the host's math/rand stream).
+/* The reference draws everything from Go's global math/rand stream (main_cpu.go:1367).  The uint64
+ * SOURCE is injectable; the derived draws (Int63, Int31, Float64, Intn) restate Go's math/rand v1
+ * derivations on top of whichever source is plugged in.
+ *   ORC_RNG_ALFG    Go's rngSource itself: additive lagged Fibonacci (607,273) seeded as rand.Seed
+ *                   does.  Its 607-word seed table (rngCooked, Go stdlib -- not in /root/reference,
+ *                   Go not installed) is recomputed from its definition (the generator's state 7.8e12
+ *                   steps after srand(1)) by tools/gen_go_rng_cooked.py; the stream is pinned by known
+ *                   outputs of Go programs (rand.Seed(1): Int63 5577006791947779410, ..., Intn(100)
+ *                   81 87 47 59 81 18 25 40 56 0, Float64 0.6046602879796196, ...; seed 42: 5 87),
+ *                   tests/test_oracle_kat.py::test_go_math_rand_known_answers.
  *   ORC_RNG_PHILOX  counter-based Philox4x32-10 keyed by seed, one stream per
  *                   (generation, individual): the stream the CUDA selection kernel uses. */
 enum { ORC_RNG_ALFG = 0, ORC_RNG_PHILOX = 1 };

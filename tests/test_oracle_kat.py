@@ -1,8 +1,9 @@
 """Known-answer tests that pin the CPU oracle.
 
 The reference ships no usable golden vectors for this path (main_test.go does not compile at the
-reference snapshot); these hand-derived KATs plus the 4-row toy dataset of main_test.go:107-112 are
-the oracle's only anchor ("parity unpinned").
+reference snapshot); these hand-derived KATs plus the 4-row toy dataset of main_test.go:107-112 anchor the
+arithmetic ("parity unpinned" by the reference), and known outputs of real Go programs anchor the random stream
+(test_go_math_rand_known_answers: the oracle draws exactly what rand.Seed(seed), main_cpu.go:1367, would).
 """
 import math
 
