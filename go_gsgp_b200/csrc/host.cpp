@@ -1444,4 +1444,113 @@ int gsgph_writer_close(gsgph_writer *w)
     return bad ? 2 : 0;
 }
 
+// ---- -proto_dump (main_cpu.go:1416-1436,1441-1488,1510-1517; evolution.proto) --------------------------------------
+// The protobuf wire format written directly (proto3: packed repeated scalars, zero-valued scalars and empty
+// bytes / repeated fields left out, fields in number order -- what proto.Marshal emits for these messages).
+struct gsgph_proto {
+    std::string evo, pop, ind, rt;       // serialized Evolution so far / open Population / scratch
+    bool open = false;
+    int32_t n_pop = 0;
+
+    static void varint(std::string &o, uint64_t v)
+    {
+        while (v >= 0x80) { o.push_back((char)(v | 0x80)); v >>= 7; }
+        o.push_back((char)v);
+    }
+    static void tag(std::string &o, uint32_t field, uint32_t wire) { varint(o, (uint64_t)field << 3 | wire); }
+    static void f64(std::string &o, uint32_t field, double v)                 // double field = N; (left out when +0.0)
+    {
+        uint64_t b; memcpy(&b, &v, 8);
+        if (b == 0) return;
+        tag(o, field, 1); o.append(reinterpret_cast<const char *>(&b), 8);    // little-endian host (x86-64)
+    }
+    static void packed_f64(std::string &o, uint32_t field, const double *v, int64_t n)
+    {
+        if (n <= 0) return;
+        tag(o, field, 2); varint(o, (uint64_t)n * 8);
+        o.append(reinterpret_cast<const char *>(v), (size_t)n * 8);
+    }
+    static void packed_i32(std::string &o, uint32_t field, const int32_t *v, int64_t n, std::string &tmp)
+    {
+        if (n <= 0) return;
+        tmp.clear();
+        for (int64_t i = 0; i < n; ++i) varint(tmp, (uint64_t)(int64_t)v[i]); // int32: sign-extended to 64 bits
+        tag(o, field, 2); varint(o, tmp.size()); o.append(tmp);
+    }
+    static void bytes(std::string &o, uint32_t field, const char *v, size_t n)
+    {
+        tag(o, field, 2); varint(o, n); o.append(v, n);
+    }
+};
+
+gsgph_proto *gsgph_proto_new(void) { return new gsgph_proto(); }
+void gsgph_proto_free(gsgph_proto *d) { delete d; }
+
+int gsgph_proto_begin_population(gsgph_proto *d, int32_t generation)
+{
+    if (!d || d->open) return 1;
+    d->open = true;
+    d->pop.clear();
+    if (generation != 0) { gsgph_proto::tag(d->pop, 1, 0); gsgph_proto::varint(d->pop, (uint64_t)(int64_t)generation); }
+    return 0;
+}
+
+int gsgph_proto_add_individual(gsgph_proto *d, int32_t op, double fitness_train, double fitness_test,
+                               const double *semantic_train, int64_t nrow, const double *semantic_test, int64_t nrow_test,
+                               const uint8_t *contrib, int64_t contrib_len,
+                               int32_t n_rt, const int32_t *const *rt_data, const int32_t *rt_len,
+                               const double *const *rt_semantic_train, const double *const *rt_semantic_test)
+{
+    if (!d || !d->open || op < 0 || op > 3 || nrow < 0 || nrow_test < 0 || contrib_len < 0 || n_rt < 0) return 1;
+    if ((nrow > 0 && !semantic_train) || (nrow_test > 0 && !semantic_test) || (contrib_len > 0 && !contrib)) return 1;
+    if (n_rt > 0 && (!rt_data || !rt_len)) return 1;
+    std::string &o = d->ind;
+    o.clear();
+    if (op != 0) { gsgph_proto::tag(o, 1, 0); gsgph_proto::varint(o, (uint64_t)op); }
+    gsgph_proto::f64(o, 2, fitness_train);
+    gsgph_proto::f64(o, 3, fitness_test);
+    gsgph_proto::packed_f64(o, 4, semantic_train, nrow);
+    gsgph_proto::packed_f64(o, 5, semantic_test, nrow_test);
+    if (contrib_len > 0) gsgph_proto::bytes(o, 6, reinterpret_cast<const char *>(contrib), (size_t)contrib_len);
+    std::string tmp;
+    for (int32_t t = 0; t < n_rt; ++t) {                                       // RandomTree{data, semantic_train, semantic_test}
+        if (rt_len[t] < 0 || (rt_len[t] > 0 && !rt_data[t])) return 1;
+        d->rt.clear();
+        gsgph_proto::packed_i32(d->rt, 1, rt_data[t], rt_len[t], tmp);
+        if (rt_semantic_train && rt_semantic_train[t]) gsgph_proto::packed_f64(d->rt, 2, rt_semantic_train[t], nrow);
+        if (rt_semantic_test && rt_semantic_test[t]) gsgph_proto::packed_f64(d->rt, 3, rt_semantic_test[t], nrow_test);
+        gsgph_proto::bytes(o, 7, d->rt.data(), d->rt.size());
+    }
+    gsgph_proto::bytes(d->pop, 2, o.data(), o.size());
+    return 0;
+}
+
+int gsgph_proto_end_population(gsgph_proto *d)
+{
+    if (!d || !d->open) return 1;
+    gsgph_proto::bytes(d->evo, 1, d->pop.data(), d->pop.size());
+    d->pop.clear();
+    d->open = false;
+    ++d->n_pop;
+    return 0;
+}
+
+int64_t gsgph_proto_size(const gsgph_proto *d) { return d ? (int64_t)d->evo.size() : -1; }
+
+int gsgph_proto_bytes(const gsgph_proto *d, uint8_t *out, int64_t cap)
+{
+    if (!d || d->open || (!out && cap > 0) || cap < (int64_t)d->evo.size()) return 1;
+    if (!d->evo.empty()) memcpy(out, d->evo.data(), d->evo.size());
+    return 0;
+}
+
+int gsgph_proto_write(const gsgph_proto *d, const char *path)
+{
+    if (!d || d->open || !path) return 1;
+    FILE *f = fopen(path, "wb");
+    if (!f) return 2;
+    const bool ok = d->evo.empty() || fwrite(d->evo.data(), 1, d->evo.size(), f) == d->evo.size();
+    return (fclose(f) == 0 && ok) ? 0 : 2;
+}
+
 }  // extern "C"

@@ -3,6 +3,7 @@ per-generation plan) used by the Python harness and mirrored by the C++ CLI driv
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -60,6 +61,17 @@ HOST_SIGNATURES = {
     "gsgph_writer_float": (C.c_int, [C.c_void_p, C.c_double]),
     "gsgph_writer_close": (C.c_int, [C.c_void_p]),
     "gsgph_gzip_member": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "gsgph_proto_new": (C.c_void_p, []),
+    "gsgph_proto_free": (None, [C.c_void_p]),
+    "gsgph_proto_begin_population": (C.c_int, [C.c_void_p, C.c_int32]),
+    "gsgph_proto_add_individual": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double,
+                                             C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_int64,
+                                             C.c_char_p, C.c_int64, C.c_int32, C.POINTER(C.POINTER(C.c_int32)),
+                                             C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double))]),
+    "gsgph_proto_end_population": (C.c_int, [C.c_void_p]),
+    "gsgph_proto_size": (C.c_int64, [C.c_void_p]),
+    "gsgph_proto_bytes": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "gsgph_proto_write": (C.c_int, [C.c_void_p, C.c_char_p]),
 }
 
 _bound = False
@@ -138,6 +150,96 @@ def gzip_member(data: bytes) -> bytes:
     if rc:
         raise RuntimeError(f"gsgph_gzip_member failed ({rc})")
     return buf.raw[: n.value]
+
+
+class ProtoDump:
+    """-proto_dump (main_cpu.go:1416-1436,1441-1488,1510-1517): pb.Evolution, one pb.Population per generation, written
+    in protobuf wire format by gsgph_proto_* (readable with the reference's evolution.proto).  Semantics are passed as
+    one row per individual, train cases then test cases (the store's layout)."""
+
+    def __init__(self, nrow, nrow_test):
+        self.L, self.nrow, self.nrow_test = _lib(), int(nrow), int(nrow_test)
+        self.h = self.L.gsgph_proto_new()
+        self._rt = [None, None]          # rt1 / rt2 and their semantics are globals in the reference (:217-226)
+
+    def close(self):
+        if self.h:
+            self.L.gsgph_proto_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin_population(self, generation):
+        if self.L.gsgph_proto_begin_population(self.h, int(generation)):
+            raise RuntimeError("gsgph_proto_begin_population: a population is already open")
+
+    def end_population(self):
+        if self.L.gsgph_proto_end_population(self.h):
+            raise RuntimeError("gsgph_proto_end_population: no population is open")
+
+    def add_individual(self, op, fit, fit_test, semantic, contrib=b"", trees=()):
+        """trees: up to two (data, semantic) pairs -- the operator's random trees; (None, None) is the reference's
+        not-yet-assigned rt (an empty RandomTree)"""
+        sem = np.ascontiguousarray(semantic, np.float64)
+        assert sem.shape == (self.nrow + self.nrow_test,)
+        n = len(trees)
+        keep, data = [], (C.POINTER(C.c_int32) * max(n, 1))()
+        lens = (C.c_int32 * max(n, 1))()
+        tr, te = (C.POINTER(C.c_double) * max(n, 1))(), (C.POINTER(C.c_double) * max(n, 1))()
+        for t, (d, ts) in enumerate(trees):
+            if d is None:
+                continue                                         # NULL pointers, length 0
+            d = np.ascontiguousarray(d, np.int32)
+            ts = np.ascontiguousarray(ts, np.float64)
+            assert ts.shape == sem.shape
+            keep += [d, ts]
+            data[t], lens[t] = capi.iptr(d), len(d)
+            tr[t] = capi.dptr(ts)
+            te[t] = C.cast(C.c_void_p(ts.ctypes.data + 8 * self.nrow), C.POINTER(C.c_double))
+        test = C.cast(C.c_void_p(sem.ctypes.data + 8 * self.nrow), C.POINTER(C.c_double))
+        rc = self.L.gsgph_proto_add_individual(self.h, int(op), float(fit), float(fit_test), capi.dptr(sem), self.nrow, test,
+                                               self.nrow_test, bytes(contrib), len(contrib), n, data, lens, tr, te)
+        if rc:
+            raise RuntimeError("gsgph_proto_add_individual: bad arguments or no open population")
+
+    def add_initial_population(self, fit, fit_test, semantics, contribs=None):
+        """generation 0 (:1418-1436): every individual is Individual_INIT, no random trees"""
+        self.begin_population(0)
+        for k in range(len(fit)):
+            self.add_individual(capi.OP_INIT, fit[k], fit_test[k], semantics[k], contribs[k] if contribs else b"")
+        self.end_population()
+
+    def add_generation(self, generation, plan, pool, fit_new, fit_test_new, semantics_new, tree_semantic, contribs=None):
+        """one generation's loop (:1441-1488) from the plan that produced it.  tree_semantic(k, which) -> the semantic of
+        individual k's random tree (Engine.get_tree_semantic with GSGP_FLAG_KEEP_TREE_SEMANTICS).  The elite creates no
+        tree, so -- as in the reference, where rt1 / rt2 are globals -- its entry repeats the previous individual's."""
+        self.begin_population(generation)
+        for k in range(len(plan)):
+            e = plan[k]
+            op = int(e["op"])
+            if op in (capi.OP_XO, capi.OP_MUT) and not e["elite"]:
+                self._rt[0] = (pool[e["tree0_off"]: e["tree0_off"] + e["tree0_len"]].copy(), tree_semantic(k, 0))
+                if op == capi.OP_MUT:
+                    self._rt[1] = (pool[e["tree1_off"]: e["tree1_off"] + e["tree1_len"]].copy(), tree_semantic(k, 1))
+            trees = [r if r is not None else (None, None) for r in self._rt[: {capi.OP_XO: 1, capi.OP_MUT: 2}.get(op, 0)]]
+            self.add_individual(op, fit_new[k], fit_test_new[k], semantics_new[k], contribs[k] if contribs else b"", trees)
+        self.end_population()
+
+    def tobytes(self) -> bytes:
+        n = self.L.gsgph_proto_size(self.h)
+        buf = C.create_string_buffer(max(n, 1))
+        if self.L.gsgph_proto_bytes(self.h, buf, n):
+            raise RuntimeError("gsgph_proto_bytes: a population is still open")
+        return buf.raw[:n]
+
+    def write(self, path):
+        rc = self.L.gsgph_proto_write(self.h, os.fsencode(path))
+        if rc:
+            raise OSError(f"gsgph_proto_write failed ({rc}): {path}")
 
 
 class LineWriter:

@@ -143,6 +143,29 @@ int gsgph_writer_close(gsgph_writer *w);
  * whose code would exceed 15 bits.  cap >= n + n/8 + 512 always suffices; 3: cap too small (len_out = needed). */
 int gsgph_gzip_member(const char *src, int64_t n, char *out, int64_t cap, int64_t *len_out);
 
+/* ---- -proto_dump (main_cpu.go:1416-1436,1441-1488,1510-1517; messages of evolution.proto) ------------------------
+ * pb.Evolution built population by population and written in the protobuf wire format proto.Marshal produces (proto3:
+ * packed repeated scalars, zero scalars / empty fields left out), so the reference's analysis tooling reads the file
+ * unchanged.  One population is open at a time: begin, add every individual in index order, end.
+ *   op                 pb.Individual_Operator: 0 INIT, 1 XO, 2 MUT, 3 REPR (:1425,1454,1460,1468)
+ *   contrib            contrib[k].AsBytes() of the host's bookkeeping (may be NULL / 0)
+ *   rt_*               the operator's random trees {rt, sem_rt_train, sem_rt_test} (:1456-1466): n_rt = 0, 1 or 2;
+ *                      rt_semantic_train[t] has nrow values, rt_semantic_test[t] nrow_test (either array may be NULL)
+ * All pointers are read during the call only.  Non-zero: bad arguments / wrong call order; gsgph_proto_write 2: I/O. */
+typedef struct gsgph_proto gsgph_proto;
+gsgph_proto *gsgph_proto_new(void);                                            /* new(pb.Evolution) :1419 */
+void gsgph_proto_free(gsgph_proto *d);
+int gsgph_proto_begin_population(gsgph_proto *d, int32_t generation);          /* new(pb.Population) :1420-1421,1443-1444 */
+int gsgph_proto_add_individual(gsgph_proto *d, int32_t op, double fitness_train, double fitness_test,
+                               const double *semantic_train, int64_t nrow, const double *semantic_test, int64_t nrow_test,
+                               const uint8_t *contrib, int64_t contrib_len,
+                               int32_t n_rt, const int32_t *const *rt_data, const int32_t *rt_len,
+                               const double *const *rt_semantic_train, const double *const *rt_semantic_test);
+int gsgph_proto_end_population(gsgph_proto *d);                                /* append(pb_evo.Generations, pb_pop) :1436,1487 */
+int64_t gsgph_proto_size(const gsgph_proto *d);                                /* bytes of the closed populations so far */
+int gsgph_proto_bytes(const gsgph_proto *d, uint8_t *out, int64_t cap);        /* proto.Marshal(pb_evo) :1511 */
+int gsgph_proto_write(const gsgph_proto *d, const char *path);                 /* ioutil.WriteFile :1515 */
+
 #ifdef __cplusplus
 }
 #endif
