@@ -69,7 +69,18 @@ int main(int argc, char **argv)
     gsgph_writer *f_train = gsgph_writer_open((out_dir + "/fitnesstrain.txt").c_str(), 0), *f_test = gsgph_writer_open((out_dir + "/fitnesstest.txt").c_str(), 0);
     gsgph_writer *s_train = gsgph_writer_open((out_dir + "/semantic_train.txt").c_str(), 0), *s_test = gsgph_writer_open((out_dir + "/semantic_test.txt").c_str(), 0);
     if (!f_train || !f_test || !s_train || !s_test) { fprintf(stderr, "panic: cannot create the output files\n"); return 2; }
+    // contributions (:1390-1397,1411,1503): which seeded model each individual descends from, updated from every plan
+    gsgph_contrib *contrib = gsgph_contrib_new(pop, n_seeds);
+    FILE *f_contrib = fopen((out_dir + "/contributions.txt").c_str(), "w");
+    if (!contrib || !f_contrib) { fprintf(stderr, "panic: cannot create the contributions file\n"); return 2; }
+    std::vector<char> line(64);
     auto write_best = [&] {                                                     // :1404-1411, :1494-1503
+        int64_t need = 0;
+        if (gsgph_contrib_format(contrib, index_best, line.data(), (int64_t)line.size(), &need) == 3) {
+            line.resize((size_t)need);
+            gsgph_contrib_format(contrib, index_best, line.data(), (int64_t)line.size(), &need);
+        }
+        fwrite(line.data(), 1, (size_t)need, f_contrib); fputc('\n', f_contrib);
         gsgph_writer_float(f_train, fit[(size_t)index_best]);
         gsgph_writer_float(f_test, fit_test[(size_t)index_best]);
         if (gsgp_get_semantic(ctx, index_best, sem.data())) die(ctx, "gsgp_get_semantic");
@@ -91,12 +102,15 @@ int main(int argc, char **argv)
         gsgph_planner_programs(planner, &programs, &n_ins, &prog_off, &prog_desc);
         if (gsgp_generation_compiled(ctx, plan, trees, tlen, programs, n_ins, prog_off, prog_desc,
                                      fit.data(), fit_test.data(), &index_best)) die(ctx, "gsgp_generation_compiled");
+        if (gsgph_contrib_apply(contrib, plan, 0)) { fprintf(stderr, "panic: contributions\n"); return 2; }   // :857,885,909,1196
         write_best();
     }
     gsgph_planner_free(planner);
     if (gsgph_writer_close(f_train) | gsgph_writer_close(f_test) | gsgph_writer_close(s_train) | gsgph_writer_close(s_test)) {
         fprintf(stderr, "panic: cannot write the output files\n"); return 2;
     }
+    if (fclose(f_contrib) != 0) { fprintf(stderr, "panic: cannot write the contributions file\n"); return 2; }
+    gsgph_contrib_free(contrib);
     gsgp_destroy(ctx);
     gsgph_rng_free(rng);
     gsgph_free(set);

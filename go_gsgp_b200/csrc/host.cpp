@@ -1553,4 +1553,135 @@ int gsgph_proto_write(const gsgph_proto *d, const char *path)
     return (fclose(f) == 0 && ok) ? 0 : 2;
 }
 
+// ---- contributions (main_cpu.go:128-149,857,863-873,885,909,1196,1272-1283,1390-1397,1411,1503) ---------------------
+// contrib[k] is a vector of num_models big integers: crossover adds the parents' vectors, everything else copies one.
+// The values at most double per generation, so they are kept as fixed-width little-endian limb arrays [P][M][W] that
+// widen by one limb when an addition carries out of the top (every ~64 generations) instead of as heap big.Ints.
+struct gsgph_contrib {
+    int32_t P = 0, M = 0, W = 1;
+    std::vector<uint64_t> cur, nxt;
+
+    void widen()                                                              // W -> W + 1 on `cur`
+    {
+        const size_t n = (size_t)P * M;
+        std::vector<uint64_t> w(n * (size_t)(W + 1), 0);
+        for (size_t i = 0; i < n; ++i) memcpy(&w[i * (size_t)(W + 1)], &cur[i * (size_t)W], (size_t)W * 8);
+        cur.swap(w);
+        ++W;
+        nxt.assign(cur.size(), 0);
+    }
+    // rows [k0, k1) of the next generation; returns false if an addition carried out of the top limb
+    bool rows(const gsgp_plan_entry *plan, int32_t k0, int32_t k1)
+    {
+        const size_t row = (size_t)M * W;
+        bool ok = true;
+        for (int32_t k = k0; k < k1; ++k) {
+            const gsgp_plan_entry &e = plan[k];
+            uint64_t *d = &nxt[(size_t)k * row];
+            const uint64_t *a = &cur[(size_t)e.p1 * row];
+            if (e.op == GSGP_OP_XO && !e.elite) {                             // merge_contribs :869-873,885
+                const uint64_t *b = &cur[(size_t)e.p2 * row];
+                if (W == 1) {
+                    uint64_t over = 0;
+                    for (size_t i = 0; i < row; ++i) { d[i] = a[i] + b[i]; over |= (d[i] < a[i]); }
+                    ok = ok && !over;
+                } else {
+                    for (int32_t m = 0; m < M; ++m) {
+                        uint64_t carry = 0;
+                        for (int32_t w = 0; w < W; ++w) {
+                            const size_t i = (size_t)m * W + w;
+                            const uint64_t t = a[i] + b[i], u = t + carry;
+                            carry = (uint64_t)(t < a[i]) | (uint64_t)(u < t);
+                            d[i] = u;
+                        }
+                        ok = ok && !carry;
+                    }
+                }
+            } else {
+                memcpy(d, a, row * 8);                                        // copy_contrib :857,863-867,909
+            }
+        }
+        return ok;
+    }
+};
+
+gsgph_contrib *gsgph_contrib_new(int32_t population_size, int32_t n_seeds)
+{
+    if (population_size < 1 || n_seeds < 0 || n_seeds > population_size) return nullptr;
+    gsgph_contrib *c = new gsgph_contrib();
+    c->P = population_size; c->M = n_seeds + 1;                               // init_tables(len(sem_seed) + 1) :1380
+    c->cur.assign((size_t)c->P * c->M, 0);
+    c->nxt.assign(c->cur.size(), 0);
+    for (int32_t i = 0; i < c->P; ++i) c->cur[(size_t)i * c->M + (i < n_seeds ? i + 1 : 0)] = 1;   // :1390-1397
+    return c;
+}
+void gsgph_contrib_free(gsgph_contrib *c) { delete c; }
+int32_t gsgph_contrib_num_models(const gsgph_contrib *c) { return c ? c->M : -1; }
+int32_t gsgph_contrib_limbs(const gsgph_contrib *c) { return c ? c->W : -1; }
+
+int gsgph_contrib_apply(gsgph_contrib *c, const gsgp_plan_entry *plan, int32_t n_threads)
+{
+    if (!c || !plan) return 1;
+    for (int32_t k = 0; k < c->P; ++k) {
+        const gsgp_plan_entry &e = plan[k];
+        if (e.p1 < 0 || e.p1 >= c->P) return 2;
+        if (e.op == GSGP_OP_XO && !e.elite && (e.p2 < 0 || e.p2 >= c->P)) return 2;
+    }
+    if (n_threads <= 0) n_threads = (int32_t)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if ((int64_t)c->P * c->M * c->W < (1 << 16)) n_threads = 1;               // small tables: not worth the threads
+    n_threads = std::min(n_threads, c->P);
+    for (;;) {
+        bool ok = true;
+        if (n_threads == 1) ok = c->rows(plan, 0, c->P);
+        else {
+            std::vector<std::thread> th;
+            std::vector<char> oks((size_t)n_threads, 1);
+            for (int32_t t = 0; t < n_threads; ++t)
+                th.emplace_back([&, t] { oks[(size_t)t] = c->rows(plan, (int32_t)((int64_t)c->P * t / n_threads), (int32_t)((int64_t)c->P * (t + 1) / n_threads)); });
+            for (auto &x : th) x.join();
+            for (char o : oks) ok = ok && o;
+        }
+        if (ok) break;
+        c->widen();                                                           // a value outgrew W limbs: redo one limb wider
+    }
+    c->cur.swap(c->nxt);                                                      // update_tables :1196
+    return 0;
+}
+
+// Contribution.String() (:141-146): the decimal values joined by commas
+int gsgph_contrib_format(const gsgph_contrib *c, int32_t ind, char *out, int64_t cap, int64_t *len_out)
+{
+    if (!c || ind < 0 || ind >= c->P || (!out && cap > 0)) return 1;
+    std::string s;
+    std::vector<uint64_t> v((size_t)c->W);
+    std::vector<uint64_t> chunks;
+    for (int32_t m = 0; m < c->M; ++m) {
+        memcpy(v.data(), &c->cur[((size_t)ind * c->M + m) * (size_t)c->W], (size_t)c->W * 8);
+        int32_t top = c->W;
+        chunks.clear();
+        while (top > 0 && v[(size_t)top - 1] == 0) --top;
+        while (top > 0) {                                                     // divide by 10^19, most significant limb first
+            unsigned __int128 rem = 0;
+            for (int32_t w = top - 1; w >= 0; --w) {
+                const unsigned __int128 x = (rem << 64) | v[(size_t)w];
+                v[(size_t)w] = (uint64_t)(x / 10000000000000000000ull);
+                rem = x % 10000000000000000000ull;
+            }
+            chunks.push_back((uint64_t)rem);
+            while (top > 0 && v[(size_t)top - 1] == 0) --top;
+        }
+        if (m) s.push_back(',');
+        if (chunks.empty()) s.push_back('0');
+        else {
+            char b[24];
+            s.append(b, (size_t)snprintf(b, sizeof b, "%llu", (unsigned long long)chunks.back()));
+            for (size_t i = chunks.size() - 1; i-- > 0;) s.append(b, (size_t)snprintf(b, sizeof b, "%019llu", (unsigned long long)chunks[i]));
+        }
+    }
+    if (len_out) *len_out = (int64_t)s.size();
+    if ((int64_t)s.size() > cap) return 3;
+    memcpy(out, s.data(), s.size());
+    return 0;
+}
+
 }  // extern "C"

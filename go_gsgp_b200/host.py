@@ -61,6 +61,12 @@ HOST_SIGNATURES = {
     "gsgph_writer_float": (C.c_int, [C.c_void_p, C.c_double]),
     "gsgph_writer_close": (C.c_int, [C.c_void_p]),
     "gsgph_gzip_member": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "gsgph_contrib_new": (C.c_void_p, [C.c_int32, C.c_int32]),
+    "gsgph_contrib_free": (None, [C.c_void_p]),
+    "gsgph_contrib_num_models": (C.c_int32, [C.c_void_p]),
+    "gsgph_contrib_limbs": (C.c_int32, [C.c_void_p]),
+    "gsgph_contrib_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "gsgph_contrib_format": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "gsgph_proto_new": (C.c_void_p, []),
     "gsgph_proto_free": (None, [C.c_void_p]),
     "gsgph_proto_begin_population": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -152,6 +158,54 @@ def gzip_member(data: bytes) -> bytes:
     return buf.raw[: n.value]
 
 
+class Contributions:
+    """contrib / contrib_new of main_cpu.go (:128-149,215-216): per individual, how often each seeded model (slot i + 1)
+    and GP itself (slot 0) appears among its ancestors.  apply(plan) is one generation (:857,885,909,1196)."""
+
+    def __init__(self, population_size, n_seeds=0):
+        self.L = _lib()
+        self.h = self.L.gsgph_contrib_new(population_size, n_seeds)
+        if not self.h:
+            raise ValueError("gsgph_contrib_new: bad sizes")
+        self.P = population_size
+
+    def close(self):
+        if self.h:
+            self.L.gsgph_contrib_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_models(self):
+        return self.L.gsgph_contrib_num_models(self.h)
+
+    @property
+    def limbs(self):
+        return self.L.gsgph_contrib_limbs(self.h)
+
+    def apply(self, plan, n_threads=0):
+        plan = np.ascontiguousarray(plan, PLAN_DTYPE)
+        assert len(plan) == self.P
+        rc = self.L.gsgph_contrib_apply(self.h, plan.ctypes.data, n_threads)
+        if rc:
+            raise ValueError(f"gsgph_contrib_apply failed ({rc})")
+
+    def format(self, ind) -> str:
+        """Contribution.String() (:141-146), e.g. "3,1,4" """
+        n = C.c_int64()
+        self.L.gsgph_contrib_format(self.h, ind, None, 0, C.byref(n))
+        buf = C.create_string_buffer(max(n.value, 1))
+        rc = self.L.gsgph_contrib_format(self.h, ind, buf, n.value, C.byref(n))
+        if rc:
+            raise ValueError(f"gsgph_contrib_format failed ({rc})")
+        return buf.raw[: n.value].decode()
+
+
 class ProtoDump:
     """-proto_dump (main_cpu.go:1416-1436,1441-1488,1510-1517): pb.Evolution, one pb.Population per generation, written
     in protobuf wire format by gsgph_proto_* (readable with the reference's evolution.proto).  Semantics are passed as
@@ -216,7 +270,9 @@ class ProtoDump:
     def add_generation(self, generation, plan, pool, fit_new, fit_test_new, semantics_new, tree_semantic, contribs=None):
         """one generation's loop (:1441-1488) from the plan that produced it.  tree_semantic(k, which) -> the semantic of
         individual k's random tree (Engine.get_tree_semantic with GSGP_FLAG_KEEP_TREE_SEMANTICS).  The elite creates no
-        tree, so -- as in the reference, where rt1 / rt2 are globals -- its entry repeats the previous individual's."""
+        tree, so -- as in the reference, where rt1 / rt2 are globals -- its entry repeats the previous individual's.
+        contribs: Contribution.String() bytes per individual; the reference passes contrib[k] of the generation being
+        replaced (:1479, before update_tables swaps the tables)."""
         self.begin_population(generation)
         for k in range(len(plan)):
             e = plan[k]

@@ -166,6 +166,24 @@ int64_t gsgph_proto_size(const gsgph_proto *d);                                /
 int gsgph_proto_bytes(const gsgph_proto *d, uint8_t *out, int64_t cap);        /* proto.Marshal(pb_evo) :1511 */
 int gsgph_proto_write(const gsgph_proto *d, const char *path);                 /* ioutil.WriteFile :1515 */
 
+/* ---- contributions (main_cpu.go:128-149: Contribution = []*big.Int, one slot per model) --------------------------
+ * Which seeded model (slot i + 1 for seed file i, slot 0 for GP itself) an individual descends from, counted with
+ * multiplicity: crossover adds the parents' vectors (merge_contribs :869-873,885), reproduction / mutation / the elite
+ * copy one (copy_contrib :857,909).  The values double per generation at most; they are kept as fixed-width limb
+ * arrays that widen on demand, so a generation of config 3 (pop 2,000 x 501 models) is one streaming pass.
+ *   gsgph_contrib_new     init_tables + the initial slots (:1272-1283,1390-1397)
+ *   gsgph_contrib_apply   one generation from its plan (op / elite / p1 / p2), then the swap of update_tables (:1196);
+ *                         2: a parent index out of range
+ *   gsgph_contrib_format  Contribution.String() of one individual (:141-146, the line written at :1411,1503 and the
+ *                         bytes of pb.Individual.contrib :1430,1479); 3: cap too small (len_out = needed) */
+typedef struct gsgph_contrib gsgph_contrib;
+gsgph_contrib *gsgph_contrib_new(int32_t population_size, int32_t n_seeds);
+void gsgph_contrib_free(gsgph_contrib *c);
+int32_t gsgph_contrib_num_models(const gsgph_contrib *c);
+int32_t gsgph_contrib_limbs(const gsgph_contrib *c);                           /* 64-bit limbs per value right now */
+int gsgph_contrib_apply(gsgph_contrib *c, const gsgp_plan_entry *plan, int32_t n_threads);
+int gsgph_contrib_format(const gsgph_contrib *c, int32_t ind, char *out, int64_t cap, int64_t *len_out);
+
 #ifdef __cplusplus
 }
 #endif

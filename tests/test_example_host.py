@@ -42,7 +42,7 @@ def test_example_host_builds_and_needs_a_device(files):
 @pytest.mark.parametrize("linsc", [0, 1])
 def test_example_host_matches_python_mirror(files, linsc):
     from go_gsgp_b200 import Engine, capi
-    from go_gsgp_b200.host import HostDriver, format_float, format_semantic
+    from go_gsgp_b200.host import Contributions, HostDriver, format_float, format_semantic
     d, X, y, nrow = files
     exe = build.build_host()
     gens, pop, seed = 5, 40, 3
@@ -56,8 +56,10 @@ def test_example_host_matches_python_mirror(files, linsc):
                use_linear_scaling=bool(linsc))
     e.set_dataset(X, y); e.set_constants(sym); e.eval_initial(0, trees)
     fit, fit_test, best = e.fitness_all()
-    ftr, fte, str_, ste = [], [], [], []
+    contrib = Contributions(pop, 0)
+    ftr, fte, str_, ste, con = [], [], [], [], []
     def record():
+        con.append(contrib.format(best))
         ftr.append(format_float(fit[best])); fte.append(format_float(fit_test[best]))
         s = e.get_semantic(best)
         str_.append(format_semantic(s[:nrow])); ste.append(format_semantic(s[nrow:]))
@@ -65,10 +67,12 @@ def test_example_host_matches_python_mirror(files, linsc):
     for _ in range(gens):
         plan, pool = host.build_plan(fit, best)
         fit, fit_test, best = e.generation(plan, pool)
+        contrib.apply(plan)
         record()
     e.close()
     assert (d / "fitnesstrain.txt").read_text().split() == ftr
     assert (d / "fitnesstest.txt").read_text().split() == fte
     assert (d / "semantic_train.txt").read_text().split() == str_
     assert (d / "semantic_test.txt").read_text().split() == ste
+    assert (d / "contributions.txt").read_text().split() == con and con[0] == "1"   # no seeds: one slot, GP itself
     assert len(ftr) == gens + 1                                # gens+1 lines (main_cpu.go:1404-1413,1494-1505)
