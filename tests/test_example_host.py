@@ -38,6 +38,48 @@ def test_example_host_builds_and_needs_a_device(files):
     assert out.returncode == 2 and "no CPU fallback" in out.stderr
 
 
+def _stub_fit(gen, k, which):                                  # tests/stub_device.c: stub_fit
+    return ((k * 2654435761 + gen * 40503 + which * 97) % 2 ** 32 % 1000) / 8.0 + 1.0
+
+
+def test_example_host_host_half_with_a_stub_device(files, tmp_path):
+    """The example's HOST half end to end on a box without a GPU: tests/stub_device.c (an LD_PRELOAD test stub, a fixed
+    hash instead of GSGP) answers the gsgp_* calls, so the program's own work is what is compared with the Python
+    mirror driven by the same fake fitness -- Go's random stream, the pipelined planner (plans equal gsgph_build_plan's,
+    visible through the contributions), contributions.txt, the asynchronous fitness / semantic writers."""
+    from go_gsgp_b200.host import Contributions, HostDriver, format_float, format_semantic
+    d, X, y, nrow = files
+    exe = build.build_host()
+    here = os.path.dirname(os.path.abspath(__file__))
+    stub = tmp_path / "libstub_device.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(stub), os.path.join(here, "stub_device.c")])
+    gens, pop, seed = 40, 50, 1
+    out = subprocess.run([exe, str(d / "train.txt"), str(d / "test.txt"), str(tmp_path), str(gens), str(pop), str(seed)],
+                         capture_output=True, text=True, env=dict(os.environ, LD_PRELOAD=str(stub)))
+    assert out.returncode == 0, out.stderr
+    host = HostDriver(population_size=pop, nvar=5, seed=seed)
+    host.create_T_F(); host.initialize_population(0)
+    contrib = Contributions(pop, 0)
+    N = len(y)
+    ftr, fte, str_, con = [], [], [], []
+    for gen in range(gens + 1):
+        fit = np.array([_stub_fit(gen, k, 0) for k in range(pop)])
+        best = int(np.argmin(fit))                             # first minimum = best_individual's strict comparison
+        if gen:
+            contrib.apply(plan)
+        con.append(contrib.format(best))
+        ftr.append(format_float(fit[best])); fte.append(format_float(_stub_fit(gen, best, 1)))
+        str_.append(format_semantic((gen + best * 0.5 + np.arange(N) * 0.25)[:nrow]))    # stub_device.c: gsgp_get_semantic
+        plan, _ = host.build_plan(fit, best)
+        plan = plan.copy()
+    assert (tmp_path / "contributions.txt").read_text().split() == con
+    assert (tmp_path / "fitnesstrain.txt").read_text().split() == ftr
+    assert (tmp_path / "fitnesstest.txt").read_text().split() == fte
+    assert (tmp_path / "semantic_train.txt").read_text().split() == str_
+    assert int(con[-1]) > 1                                    # crossovers happened: the best's lineage count grew
+    host.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("linsc", [0, 1])
 def test_example_host_matches_python_mirror(files, linsc):
