@@ -19,6 +19,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libgsgp_oracle.so")
 MSE, RMSE, MAE, MRE = 0, 1, 2, 3
 OP_INIT, OP_XO, OP_MUT, OP_REPR = 0, 1, 2, 3
 RNG_ALFG, RNG_PHILOX = 0, 1
+EXP_LIBM, EXP_GO_PORTABLE = 0, 1
 
 
 class OrcConfig(C.Structure):
@@ -113,6 +114,7 @@ def lib() -> C.CDLL:
         "orc_set_initial_tree": (None, [vp, C.c_int32, ip, C.c_int32]),
         "orc_generation": (None, [vp]),
         "orc_generation_replay": (None, [vp, C.c_void_p, ip]),
+        "orc_set_exp_kind": (None, [C.c_int]),
         "orc_exp64": (C.c_double, [C.c_double]),
         "orc_sigmoid": (C.c_double, [C.c_double]),
         "orc_create_grow_tree_arrays": (C.c_int32, [vp, C.c_int32, C.c_int32, C.c_int32, ip, C.c_int32]),

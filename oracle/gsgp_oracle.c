@@ -465,8 +465,38 @@ void orc_semantic_evaluate_array(const orc_state *s, const int32_t *tree,
 
 /* Go's math.Exp returns 1+x for |x| < 2^-28 (stdlib exp.go, NearZero); everything else is libm's
  * correctly-specialised exp.  The rule matters only for exp64's "r == 1 && v != 0" test below. */
+static int g_exp_kind = 0;
+void orc_set_exp_kind(int kind) { g_exp_kind = kind; }
+
+/* Go's portable math.Exp (stdlib exp.go: the FreeBSD e_exp.c port -- what Go runs where it has no assembly routine;
+ * amd64 / arm64 / s390x have their own), restated from its published algorithm: k = round(x / ln 2), r = x - k ln 2 in
+ * two pieces, a degree-5 rational correction, ldexp.  It differs from glibc's exp in the last bit for a few percent of
+ * the arguments: the second exp (ORC_EXP_GO_PORTABLE) exists to show what that last bit does to a run -- nothing,
+ * tests/test_oracle_kat.py::test_run_does_not_depend_on_the_last_bit_of_exp. */
+static double go_exp_portable(double x)
+{
+    const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10, Log2e = 1.44269504088896338700e+00;
+    const double Overflow = 7.09782712893383973096e+02, Underflow = -7.45133219101941108420e+02;
+    const double P1 = 1.66666666666666657415e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                 P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (isnan(x) || (isinf(x) && x > 0)) return x;
+    if (isinf(x)) return 0;
+    if (x > Overflow) return INFINITY;
+    if (x < Underflow) return 0;
+    if (x > -0x1p-28 && x < 0x1p-28) return 1 + x;
+    int k = 0;
+    if (x < 0) k = (int)(Log2e * x - 0.5);
+    else if (x > 0) k = (int)(Log2e * x + 0.5);
+    double hi = x - (double)k * Ln2Hi, lo = (double)k * Ln2Lo;
+    double r = hi - lo, t = r * r;
+    double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    double y = 1 - ((lo - (r * c) / (2 - c)) - hi);
+    return ldexp(y, k);
+}
+
 static inline double go_exp(double x)
 {
+    if (g_exp_kind == ORC_EXP_GO_PORTABLE) return go_exp_portable(x);
     if (x > -0x1p-28 && x < 0x1p-28) return 1 + x;
     return exp(x);
 }

@@ -122,6 +122,10 @@ void orc_generation(orc_state *s);
 void orc_generation_replay(orc_state *s, const orc_plan_entry *plan, const int32_t *tree_pool);
 
 /* ------------------------------------------------------------------ primitives ----------- */
+/* which exp sits under exp64 (process-wide; tests only): glibc's exp + Go's |x| < 2^-28 rule (default), or Go's portable
+ * math.Exp restated.  Go's own exp is not glibc's; both are accurate to under an ulp (see gsgp_oracle.c). */
+enum { ORC_EXP_LIBM = 0, ORC_EXP_GO_PORTABLE = 1 };
+void    orc_set_exp_kind(int kind);
 double  orc_exp64(double v);                                              /* main_cpu.go:50-61   */
 double  orc_sigmoid(double r);                                            /* :894                */
 int32_t orc_create_grow_tree_arrays(orc_state *s, int32_t depth, int32_t max_depth,
