@@ -393,6 +393,20 @@ def main():
                             "HBM-bound; see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
                 "gs_kernel_unfused": gs_unfused}
 
+    # interpreter work per generation (quoted for config 4): random trees and tree nodes evaluated over every
+    # case, counted from the last generation's plan (a pointer-prefix array of L ints holds (L + 1) / 2 nodes)
+    try:
+        lens = np.concatenate([plan["tree0_len"][computed],
+                               plan["tree1_len"][computed & (plan["op"] == capi.OP_MUT)]]).astype(np.int64)
+        lens = lens[lens > 0]
+        n_trees, n_nodes = int(len(lens)), int(np.sum((lens + 1) // 2))
+        per_s = float(n_global) * K / (ms_dev * 1e-3)
+        roofline["interpreter_work"] = {"trees_per_generation": n_trees, "nodes_per_generation": n_nodes,
+                                        "tree_cases_per_s": n_trees * per_s, "node_cases_per_s": n_nodes * per_s,
+                                        "note": "whole job, inside the timed generations (fused into gen_kernel)"}
+    except Exception as ex:                                  # reporting only: never costs the bench line
+        roofline["interpreter_work"] = {"error": repr(ex)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import binding as ob
