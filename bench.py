@@ -239,6 +239,8 @@ def main():
     seed_rng = np.random.Generator(np.random.PCG64(20261019 + 100 * w["cfg_id"]))
     seeds = [y + seed_rng.normal(0.0, 0.05 + 0.001 * k, size=n_global) for k in range(n_seeds)]   # semantic feeding
 
+    init_ms = []
+
     def setup(rng_mode, pipeline="fused"):
         os.environ["GSGP_PIPELINE"] = pipeline            # read by gsgp_create
         e = Engine(rng_mode=rng_mode, nccl_id=fresh_nccl_id(), **common)
@@ -246,8 +248,10 @@ def main():
         e.set_constants(sym)
         for k, sem in enumerate(seeds):                    # main_cpu.go:1383-1388
             e.seed_semantic(k, sem)
+        t0 = time.perf_counter()
         e.eval_initial(n_seeds, init_trees)
         fit, fit_test, best = e.fitness_all()
+        init_ms.append((time.perf_counter() - t0) * 1e3)    # the initial population, reported apart from the loop
         return e, fit, best
 
     K, W = args.steps, args.warmup
@@ -434,6 +438,9 @@ def main():
                                       planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)"},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "init": {"ms": init_ms[0] if init_ms else None,
+                     "what": "evaluate() of the initial population (main_cpu.go:780-795: %d trees over every case + fitness + best), "
+                             "host wall clock with the tree upload; not part of `value`" % (P - n_seeds)},
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
