@@ -421,6 +421,12 @@ def main():
         cpu_baseline = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_baseline_gens} generations at {n_local} cases, population subsample {pop_s} "
                                   f"(cost linear in pop), {dt:.1f} s; C restatement of main_cpu.go, not go-gsgp"}
+        try:                                                 # and with -workers 1 (SURVEY 8d asks for both)
+            pop_1 = max(8, pop_s // 8)
+            v1, dt1 = oracle_arm(w, n_local, pop_1, args.cpu_baseline_gens, 0, 1)
+            cpu_baseline["single_thread"] = {"value": v1, "cores": 1, "sample": f"population subsample {pop_1}, {dt1:.1f} s"}
+        except Exception as ex:
+            cpu_baseline["single_thread"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {
