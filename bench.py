@@ -313,18 +313,46 @@ def main():
     planner_mode = os.environ.get("GSGP_BENCH_PLANNER", "programs")          # "0": serial gsgph_build_plan, "1": draws only
     # one process per GPU shares the box's cores: the planner's compile threads scale down with the world size
     planner_threads = max(1, min(4, (os.cpu_count() or 4) // (4 * world)))
-    planner = host.planner(programs=planner_mode == "programs", n_threads=planner_threads) if planner_mode != "0" else None
+    # GSGP_BENCH_SHARE_PLAN=1 (N > 1, opt-in until measured on a multi-GPU box): rank 0 alone plans and the other ranks take
+    # plan + trees + programs from shared memory (gsgph_channel_*) instead of every rank running a planner
+    share = world > 1 and planner_mode == "programs" and os.environ.get("GSGP_BENCH_SHARE_PLAN", "0") == "1"
+    channel, seq_next = None, 1
+    if share:
+        from go_gsgp_b200.host import PlanChannel
+        ch_name = "/gsgp_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        tree_cap = 4 * (1 << max(w["depth"], 1))
+        if rank == 0:
+            channel = PlanChannel.create(ch_name, P, 2 * P * tree_cap, 2 * P * (tree_cap // 4 + 1), world - 1)
+            planner_threads = max(1, min(4, (os.cpu_count() or 4) // 4))
+        barrier()
+        if rank != 0:
+            channel = PlanChannel.attach(ch_name, rank - 1, P, timeout_ms=60000)
+    planner = None if (share and rank != 0) else (
+        host.planner(programs=planner_mode == "programs", n_threads=planner_threads) if planner_mode != "0" else None)
     def replay_step(count=False):
-        nonlocal fit, best, h2d, d2h
-        if planner is not None:
-            plan, pool = planner.plan(fit, best)
-            planner.prefetch(best)
+        nonlocal fit, best, h2d, d2h, seq_next
+        if share:                                            # one generation through the channel, stepped from Python
+            if rank == 0:
+                plan, pool = planner.plan(fit, best)
+                progs = planner.programs()
+                channel.publish(seq_next, plan, pool, *progs, timeout_ms=60000)
+                planner.prefetch(best)
+            else:
+                plan, pool, *progs = channel.acquire(seq_next, timeout_ms=60000)
+            fit, fit_test, best = e.generation_compiled(plan, pool, *progs)
+            if rank != 0:
+                channel.release(seq_next)
+            seq_next += 1
         else:
-            plan, pool = host.build_plan(fit, best)
-        if planner_mode == "programs":
-            fit, fit_test, best = e.generation_compiled(plan, pool, *planner.programs())
-        else:
-            fit, fit_test, best = e.generation(plan, pool)
+            if planner is not None:
+                plan, pool = planner.plan(fit, best)
+                planner.prefetch(best)
+            else:
+                plan, pool = host.build_plan(fit, best)
+            if planner_mode == "programs":
+                fit, fit_test, best = e.generation_compiled(plan, pool, *planner.programs())
+            else:
+                fit, fit_test, best = e.generation(plan, pool)
         if count:
             # uploaded by the call: plan entries, accumulator programs (8 B per function node; a tree of i ints
             # has (i-1)/4 function nodes), program offset/descriptor tables; read back: 2 fitness vectors + best
@@ -334,11 +362,14 @@ def main():
             d2h = 16 * P + 4
     # the loop itself runs in the compiled host (gsgph_replay_generations: plan -> gsgp_generation_compiled -> fitness
     # back, K times), like a Go / C++ main would; GSGP_BENCH_E2E_LOOP=python steps it from Python instead
-    compiled_loop = planner is not None and os.environ.get("GSGP_BENCH_E2E_LOOP", "compiled") == "compiled"
+    compiled_loop = (planner is not None or share) and os.environ.get("GSGP_BENCH_E2E_LOOP", "compiled") == "compiled"
     fit_test = np.zeros_like(fit)
     def replay(n):
-        nonlocal fit, fit_test, best
-        if compiled_loop:
+        nonlocal fit, fit_test, best, seq_next
+        if compiled_loop and share:
+            fit, fit_test, best, _, _ = channel.replay_generations(planner, e, seq_next, n, fit, fit_test, best)
+            seq_next += n
+        elif compiled_loop:
             fit, fit_test, best, _, _ = planner.replay_generations(e, n, fit, fit_test, best)
         else:
             for _ in range(n):
@@ -354,6 +385,9 @@ def main():
     e2e_value = updates_per_step * K / (ms_e2e * 1e-3)
     planner_stats = planner.stats() if planner is not None else None
     e.close()
+    if channel is not None:
+        barrier()                                            # every reader is done before rank 0 unlinks the segment
+        channel.close()
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
@@ -441,7 +475,9 @@ def main():
                     "ms_per_step": ms_e2e / K, "timing": "host wall clock around K generations of the host-replay loop (plan building + gsgp_generation%s with host buffers), loop in %s" % ("_compiled" if planner_mode == "programs" else "", "the compiled host (gsgph_replay_generations)" if compiled_loop else "Python"),
                     "plan_builder": ("pipelined (gsgph_planner_*%s): elite-index guesses right/wrong = %d/%d" %
                                      (", trees compiled ahead: gsgp_generation_compiled" if planner_mode == "programs" else "",
-                                      planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)"},
+                                      planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)",
+                    "plan_sharing": "rank 0 plans, the other ranks read the plan from shared memory (gsgph_channel_*)" if share
+                                    else ("every rank builds the same plan" if world > 1 else "n/a")},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "init": {"ms": init_ms[0] if init_ms else None,

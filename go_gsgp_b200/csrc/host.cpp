@@ -14,6 +14,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <new>
 #include <charconv>
 #include <condition_variable>
 #include <deque>
@@ -851,6 +854,195 @@ int gsgph_replay_generations(gsgph_planner *pl, gsgp_ctx *ctx, int32_t n_generat
             rc = gsgp_generation_compiled(ctx, plan, pool, pool_len, reinterpret_cast<const uint32_t *>(B.prog.data()), B.n_ins,
                                           B.prog_off.data(), B.prog_desc.data(), fit, fit_test, index_best);
         } else rc = gsgp_generation(ctx, plan, pool, pool_len, fit, fit_test, index_best);
+        if (rc) return 4;                                                       // gsgp_last_error(ctx) says why
+        if (best_fit_history) best_fit_history[g] = fit[*index_best];           // :1495-1496
+        if (best_fit_test_history) best_fit_test_history[g] = fit_test[*index_best];
+    }
+    return 0;
+}
+
+// ---- one plan for every rank of a node ("host broadcasts the same plan to each GPU") ------------------------
+// The plan of a generation is identical on every rank, so one process (the writer) builds it and the others (readers)
+// take it from a POSIX shared-memory segment instead of each running a planner and its compile threads.  Two slots:
+// sequence s lives in slot s & 1; the writer reuses a slot once every reader has released sequence s - 2.
+}  // extern "C"  (the struct has a member template)
+struct gsgph_channel {
+    static constexpr int kMaxReaders = 64;
+    struct Header {
+        uint64_t magic;
+        int32_t P, cap_pool, cap_ins, n_readers;
+        uint64_t slot_bytes, total_bytes;
+        std::atomic<uint64_t> ready;                     // 1 once the writer has initialised the segment
+        std::atomic<uint64_t> published[2];              // the sequence number each slot holds (0: none yet)
+        std::atomic<uint64_t> released[kMaxReaders];     // the highest sequence each reader has released
+    };
+    static constexpr uint64_t kMagic = 0x67736770706c616eull;   // "gsgpplan"
+    Header *h = nullptr;
+    unsigned char *base = nullptr;
+    std::string name;
+    bool writer = false;
+    int32_t reader = -1;
+
+    static size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
+    static size_t header_bytes() { return align64(sizeof(Header)); }
+    // slot: [pool_len, n_ins][plan P][prog_off 2P][prog_desc 2P][pool cap_pool][programs 2 x cap_ins]
+    size_t off_plan() const { return 64; }
+    size_t off_poff() const { return off_plan() + align64(sizeof(gsgp_plan_entry) * (size_t)h->P); }
+    size_t off_pdesc() const { return off_poff() + align64(8 * (size_t)h->P); }
+    size_t off_pool() const { return off_pdesc() + align64(8 * (size_t)h->P); }
+    size_t off_prog() const { return off_pool() + align64(4 * (size_t)h->cap_pool); }
+    static size_t slot_size(int32_t P, int32_t cap_pool, int32_t cap_ins)
+    {
+        return 64 + align64(sizeof(gsgp_plan_entry) * (size_t)P) + 2 * align64(8 * (size_t)P) + align64(4 * (size_t)cap_pool) +
+               align64(8 * (size_t)cap_ins);
+    }
+    unsigned char *slot(uint64_t seq) const { return base + header_bytes() + (size_t)(seq & 1) * h->slot_bytes; }
+
+    template <typename F> static bool wait_until(F done, int timeout_ms)      // spin briefly, then sleep in 20 us steps
+    {
+        for (int i = 0; i < 2000; ++i) { if (done()) return true; _mm_pause(); }
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            if (done()) return true;
+            if (timeout_ms >= 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(timeout_ms)) return false;
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+    }
+};
+extern "C" {
+
+gsgph_channel *gsgph_channel_create(const char *name, int32_t population_size, int32_t cap_pool_ints, int32_t cap_instructions,
+                                    int32_t n_readers)
+{
+    if (!name || population_size < 1 || cap_pool_ints < 1 || cap_instructions < 1 || n_readers < 0 ||
+        n_readers > gsgph_channel::kMaxReaders) return nullptr;
+    const size_t slot = gsgph_channel::slot_size(population_size, cap_pool_ints, cap_instructions);
+    const size_t total = gsgph_channel::header_bytes() + 2 * slot;
+    shm_unlink(name);                                                          // a stale segment of a dead run
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    if (ftruncate(fd, (off_t)total) != 0) { close(fd); shm_unlink(name); return nullptr; }
+    void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { shm_unlink(name); return nullptr; }
+    gsgph_channel *c = new gsgph_channel();
+    c->base = static_cast<unsigned char *>(m); c->h = new (m) gsgph_channel::Header();
+    c->name = name; c->writer = true;
+    c->h->magic = gsgph_channel::kMagic; c->h->P = population_size; c->h->cap_pool = cap_pool_ints; c->h->cap_ins = cap_instructions;
+    c->h->n_readers = n_readers; c->h->slot_bytes = slot; c->h->total_bytes = total;
+    c->h->published[0].store(0); c->h->published[1].store(0);
+    for (auto &r : c->h->released) r.store(0);
+    c->h->ready.store(1, std::memory_order_release);
+    return c;
+}
+
+gsgph_channel *gsgph_channel_attach(const char *name, int32_t reader_index, int32_t timeout_ms)
+{
+    if (!name || reader_index < 0 || reader_index >= gsgph_channel::kMaxReaders) return nullptr;
+    int fd = -1;
+    struct stat st{};
+    // the writer may not have created (or sized) the segment yet
+    if (!gsgph_channel::wait_until([&] {
+            if (fd < 0) fd = shm_open(name, O_RDWR, 0600);
+            return fd >= 0 && fstat(fd, &st) == 0 && (size_t)st.st_size >= gsgph_channel::header_bytes();
+        }, timeout_ms)) { if (fd >= 0) close(fd); return nullptr; }
+    void *hm = mmap(nullptr, gsgph_channel::header_bytes(), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (hm == MAP_FAILED) { close(fd); return nullptr; }
+    auto *hh = static_cast<gsgph_channel::Header *>(hm);
+    const bool ok = gsgph_channel::wait_until([&] { return hh->ready.load(std::memory_order_acquire) == 1; }, timeout_ms) &&
+                    hh->magic == gsgph_channel::kMagic && reader_index < hh->n_readers;
+    const size_t total = ok ? (size_t)hh->total_bytes : 0;
+    munmap(hm, gsgph_channel::header_bytes());
+    if (!ok) { close(fd); return nullptr; }
+    void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return nullptr;
+    gsgph_channel *c = new gsgph_channel();
+    c->base = static_cast<unsigned char *>(m); c->h = static_cast<gsgph_channel::Header *>(m);
+    c->name = name; c->reader = reader_index;
+    return c;
+}
+
+void gsgph_channel_close(gsgph_channel *c)
+{
+    if (!c) return;
+    const size_t total = (size_t)c->h->total_bytes;
+    munmap(c->base, total);
+    if (c->writer) shm_unlink(c->name.c_str());
+    delete c;
+}
+
+int gsgph_channel_publish(gsgph_channel *c, uint64_t seq, const gsgp_plan_entry *plan, const int32_t *pool, int32_t pool_len,
+                          const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off, const int32_t *prog_desc,
+                          int32_t timeout_ms)
+{
+    if (!c || !c->writer || seq < 1 || !plan || pool_len < 0 || n_instructions < 0 || (pool_len > 0 && !pool) ||
+        (n_instructions > 0 && (!programs || !prog_off || !prog_desc))) return 1;
+    if (pool_len > c->h->cap_pool || n_instructions > c->h->cap_ins) return 3;
+    const int32_t n_readers = c->h->n_readers;
+    if (seq > 2 && !gsgph_channel::wait_until([&] {                             // the slot's previous occupant is seq - 2
+            for (int32_t r = 0; r < n_readers; ++r) if (c->h->released[r].load(std::memory_order_acquire) + 2 < seq) return false;
+            return true;
+        }, timeout_ms)) return 5;
+    unsigned char *s = c->slot(seq);
+    const size_t P = (size_t)c->h->P;
+    reinterpret_cast<int32_t *>(s)[0] = pool_len; reinterpret_cast<int32_t *>(s)[1] = n_instructions;
+    memcpy(s + c->off_plan(), plan, sizeof(gsgp_plan_entry) * P);
+    if (n_instructions > 0) {
+        memcpy(s + c->off_poff(), prog_off, 8 * P);
+        memcpy(s + c->off_pdesc(), prog_desc, 8 * P);
+        memcpy(s + c->off_prog(), programs, 8 * (size_t)n_instructions);
+    }
+    if (pool_len > 0) memcpy(s + c->off_pool(), pool, 4 * (size_t)pool_len);
+    c->h->published[seq & 1].store(seq, std::memory_order_release);
+    return 0;
+}
+
+int gsgph_channel_acquire(gsgph_channel *c, uint64_t seq, const gsgp_plan_entry **plan, const int32_t **pool, int32_t *pool_len,
+                          const uint32_t **programs, int32_t *n_instructions, const int32_t **prog_off, const int32_t **prog_desc,
+                          int32_t timeout_ms)
+{
+    if (!c || c->writer || seq < 1) return 1;
+    if (!gsgph_channel::wait_until([&] { return c->h->published[seq & 1].load(std::memory_order_acquire) >= seq; }, timeout_ms)) return 5;
+    if (c->h->published[seq & 1].load(std::memory_order_acquire) != seq) return 6;   // overwritten: this reader skipped a release
+    const unsigned char *s = c->slot(seq);
+    if (plan) *plan = reinterpret_cast<const gsgp_plan_entry *>(s + c->off_plan());
+    if (pool) *pool = reinterpret_cast<const int32_t *>(s + c->off_pool());
+    if (pool_len) *pool_len = reinterpret_cast<const int32_t *>(s)[0];
+    if (programs) *programs = reinterpret_cast<const uint32_t *>(s + c->off_prog());
+    if (n_instructions) *n_instructions = reinterpret_cast<const int32_t *>(s)[1];
+    if (prog_off) *prog_off = reinterpret_cast<const int32_t *>(s + c->off_poff());
+    if (prog_desc) *prog_desc = reinterpret_cast<const int32_t *>(s + c->off_pdesc());
+    return 0;
+}
+
+int gsgph_channel_release(gsgph_channel *c, uint64_t seq)
+{
+    if (!c || c->writer || c->reader < 0) return 1;
+    c->h->released[c->reader].store(seq, std::memory_order_release);
+    return 0;
+}
+
+int gsgph_replay_generations_shared(gsgph_planner *pl, gsgph_channel *ch, gsgp_ctx *ctx, uint64_t first_seq, int32_t n_generations,
+                                    double *fit, double *fit_test, int32_t *index_best, double *best_fit_history,
+                                    double *best_fit_test_history, int32_t timeout_ms)
+{
+    if (!ch || !ctx || !fit || !fit_test || !index_best || n_generations < 0 || first_seq < 1) return 1;
+    if (ch->writer ? (!pl || !pl->programs) : pl != nullptr) return 1;         // the writer plans (programs on), readers do not
+    for (int32_t g = 0; g < n_generations; ++g) {
+        const uint64_t seq = first_seq + (uint64_t)g;
+        const gsgp_plan_entry *plan; const int32_t *pool, *prog_off, *prog_desc; const uint32_t *programs;
+        int32_t pool_len = 0, n_ins = 0;
+        if (ch->writer) {
+            if (int rc = gsgph_planner_plan(pl, fit, *index_best, &plan, &pool, &pool_len)) return rc;
+            const gsgph_planner::Buf &B = pl->buf[pl->out];
+            programs = reinterpret_cast<const uint32_t *>(B.prog.data()); n_ins = B.n_ins;
+            prog_off = B.prog_off.data(); prog_desc = B.prog_desc.data();
+            if (int rc = gsgph_channel_publish(ch, seq, plan, pool, pool_len, programs, n_ins, prog_off, prog_desc, timeout_ms)) return rc;
+            gsgph_planner_prefetch(pl, *index_best);                            // the next generation's draws start now
+        } else if (int rc = gsgph_channel_acquire(ch, seq, &plan, &pool, &pool_len, &programs, &n_ins, &prog_off, &prog_desc, timeout_ms)) return rc;
+        const int rc = gsgp_generation_compiled(ctx, plan, pool, pool_len, programs, n_ins, prog_off, prog_desc, fit, fit_test, index_best);
+        if (!ch->writer) gsgph_channel_release(ch, seq);                        // the call has copied what it needs
         if (rc) return 4;                                                       // gsgp_last_error(ctx) says why
         if (best_fit_history) best_fit_history[g] = fit[*index_best];           // :1495-1496
         if (best_fit_test_history) best_fit_test_history[g] = fit_test[*index_best];

@@ -61,6 +61,18 @@ HOST_SIGNATURES = {
     "gsgph_writer_float": (C.c_int, [C.c_void_p, C.c_double]),
     "gsgph_writer_close": (C.c_int, [C.c_void_p]),
     "gsgph_gzip_member": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "gsgph_channel_create": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "gsgph_channel_attach": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_int32]),
+    "gsgph_channel_close": (None, [C.c_void_p]),
+    "gsgph_channel_publish": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_int32,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]),
+    "gsgph_channel_acquire": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_int32)),
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                        C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)), C.c_int32]),
+    "gsgph_channel_release": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "gsgph_replay_generations_shared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double), C.c_int32]),
     "gsgph_contrib_new": (C.c_void_p, [C.c_int32, C.c_int32]),
     "gsgph_contrib_free": (None, [C.c_void_p]),
     "gsgph_contrib_num_models": (C.c_int32, [C.c_void_p]),
@@ -156,6 +168,77 @@ def gzip_member(data: bytes) -> bytes:
     if rc:
         raise RuntimeError(f"gsgph_gzip_member failed ({rc})")
     return buf.raw[: n.value]
+
+
+class PlanChannel:
+    """gsgph_channel_*: one rank (the writer) plans, the other ranks of the node read plan + tree pool + programs from
+    shared memory.  PlanChannel.create(...) on the writer, PlanChannel.attach(...) on each reader."""
+
+    def __init__(self, h, P, writer):
+        self.L, self.h, self.P, self.writer = _lib(), h, P, writer
+
+    @classmethod
+    def create(cls, name, population_size, cap_pool_ints, cap_instructions, n_readers):
+        h = _lib().gsgph_channel_create(os.fsencode(name), population_size, cap_pool_ints, cap_instructions, n_readers)
+        if not h:
+            raise OSError(f"gsgph_channel_create failed: {name}")
+        return cls(h, population_size, True)
+
+    @classmethod
+    def attach(cls, name, reader_index, population_size, timeout_ms=10000):
+        h = _lib().gsgph_channel_attach(os.fsencode(name), reader_index, timeout_ms)
+        if not h:
+            raise OSError(f"gsgph_channel_attach failed: {name}")
+        return cls(h, population_size, False)
+
+    def close(self):
+        if self.h:
+            self.L.gsgph_channel_close(self.h)
+            self.h = None
+
+    def publish(self, seq, plan, pool, programs, prog_off, prog_desc, timeout_ms=10000):
+        plan = np.ascontiguousarray(plan, PLAN_DTYPE)
+        pool = np.ascontiguousarray(pool, np.int32)
+        programs = np.ascontiguousarray(programs, np.uint32)
+        prog_off, prog_desc = np.ascontiguousarray(prog_off, np.int32), np.ascontiguousarray(prog_desc, np.int32)
+        rc = self.L.gsgph_channel_publish(self.h, seq, plan.ctypes.data, capi.iptr(pool), len(pool), programs.ctypes.data,
+                                          len(programs) // 2, capi.iptr(prog_off), capi.iptr(prog_desc), timeout_ms)
+        if rc:
+            raise RuntimeError(f"gsgph_channel_publish failed ({rc})")
+
+    def acquire(self, seq, timeout_ms=10000):
+        """-> (plan, pool, programs, prog_off, prog_desc): copies of what the writer published as `seq`"""
+        plan_p, prog_p = C.c_void_p(), C.c_void_p()
+        pool_p, off_p, desc_p = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        n_pool, n_ins = C.c_int32(), C.c_int32()
+        rc = self.L.gsgph_channel_acquire(self.h, seq, C.byref(plan_p), C.byref(pool_p), C.byref(n_pool), C.byref(prog_p),
+                                          C.byref(n_ins), C.byref(off_p), C.byref(desc_p), timeout_ms)
+        if rc:
+            raise RuntimeError(f"gsgph_channel_acquire failed ({rc})")
+        view = lambda addr, ctype, n, dt: np.ctypeslib.as_array((ctype * max(n, 1)).from_address(addr)).view(dt)[:n].copy()
+        plan = np.frombuffer((C.c_char * (40 * self.P)).from_address(plan_p.value), PLAN_DTYPE).copy()
+        return (plan, view(C.addressof(pool_p.contents), C.c_int32, n_pool.value, np.int32),
+                view(prog_p.value, C.c_uint32, 2 * n_ins.value, np.uint32),
+                view(C.addressof(off_p.contents), C.c_int32, 2 * self.P, np.int32),
+                view(C.addressof(desc_p.contents), C.c_int32, 2 * self.P, np.int32))
+
+    def release(self, seq):
+        self.L.gsgph_channel_release(self.h, seq)
+
+    def replay_generations(self, planner, engine, first_seq, n, fit, fit_test, index_best, timeout_ms=60000):
+        """gsgph_replay_generations_shared: the writer passes its Planner (programs enabled), readers pass None.
+        Returns (fit, fit_test, best, best_fit_history, best_fit_test_history)."""
+        fit, fit_test = np.array(fit, np.float64), np.array(fit_test, np.float64)
+        best = C.c_int32(int(index_best))
+        h0, h1 = np.empty(max(n, 1)), np.empty(max(n, 1))
+        rc = self.L.gsgph_replay_generations_shared(planner.h if planner is not None else None, self.h, engine.h, first_seq, n,
+                                                    capi.dptr(fit), capi.dptr(fit_test), C.byref(best), capi.dptr(h0), capi.dptr(h1),
+                                                    timeout_ms)
+        if rc == 4:
+            engine._ck(1)
+        if rc:
+            raise RuntimeError(f"gsgph_replay_generations_shared failed ({rc})")
+        return fit, fit_test, best.value, h0[:n], h1[:n]
 
 
 class Contributions:

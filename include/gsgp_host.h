@@ -89,6 +89,31 @@ int gsgph_planner_programs(const gsgph_planner *pl, const uint32_t **programs, i
  * gsgph_planner_free returns them to the stream). */
 int gsgph_replay_generations(gsgph_planner *pl, gsgp_ctx *ctx, int32_t n_generations, double *fit, double *fit_test,
                              int32_t *index_best, double *best_fit_history, double *best_fit_test_history);
+/* ---- one plan for every rank of a node (multi-GPU host replay) ------------------------------------------------------
+ * A generation's plan is identical on every rank (same RNG stream, same fitness), so one process -- the writer -- runs
+ * the planner and the others take plan + tree pool + programs from a POSIX shared-memory segment instead of each running
+ * a planner and its compile threads.  Sequence numbers start at 1 and grow by one per generation; sequence s lives in
+ * slot s & 1, which the writer reuses once every reader has released s - 2.  Pointers returned by _acquire point into
+ * the segment and stay valid until the reader releases that sequence.  timeout_ms < 0 waits for ever.
+ * Returns: 1 bad arguments, 3 plan larger than the segment's capacities, 5 timeout, 6 the slot was overwritten. */
+typedef struct gsgph_channel gsgph_channel;
+gsgph_channel *gsgph_channel_create(const char *name /* "/..." as for shm_open */, int32_t population_size,
+                                    int32_t cap_pool_ints, int32_t cap_instructions, int32_t n_readers);   /* writer */
+gsgph_channel *gsgph_channel_attach(const char *name, int32_t reader_index, int32_t timeout_ms);           /* reader */
+void gsgph_channel_close(gsgph_channel *c);                                    /* the writer also unlinks the segment */
+int gsgph_channel_publish(gsgph_channel *c, uint64_t seq, const gsgp_plan_entry *plan, const int32_t *pool, int32_t pool_len,
+                          const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off, const int32_t *prog_desc,
+                          int32_t timeout_ms);
+int gsgph_channel_acquire(gsgph_channel *c, uint64_t seq, const gsgp_plan_entry **plan, const int32_t **pool, int32_t *pool_len,
+                          const uint32_t **programs, int32_t *n_instructions, const int32_t **prog_off, const int32_t **prog_desc,
+                          int32_t timeout_ms);
+int gsgph_channel_release(gsgph_channel *c, uint64_t seq);
+/* gsgph_replay_generations across the ranks of a node: the writer (pl = its planner, programs enabled) plans, publishes
+ * and runs its own generation; a reader (pl = NULL) acquires, runs gsgp_generation_compiled and releases.  first_seq:
+ * 1 for the first call, then first_seq + n_generations of the previous call -- the same on every rank. */
+int gsgph_replay_generations_shared(gsgph_planner *pl, gsgph_channel *ch, gsgp_ctx *ctx, uint64_t first_seq, int32_t n_generations,
+                                    double *fit, double *fit_test, int32_t *index_best, double *best_fit_history,
+                                    double *best_fit_test_history, int32_t timeout_ms);
 /* the same staging for hosts that build their plans themselves (a Go host's goroutine): every tree of `plan` through
  * gsgph_compile_tree's compiler, programs concatenated in slot order (slot = 2*k + which).  programs: 2 uint32 per
  * instruction, cap instructions (pool_len / 4 + 2 * population_size always suffices); 2: malformed tree, 3: cap */

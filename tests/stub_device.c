@@ -7,7 +7,14 @@
 #include <stdlib.h>
 #include "../include/gsgp_b200.h"
 
-typedef struct { int32_t P, n, gen; } stub_ctx;
+typedef struct { int32_t P, n, gen; uint64_t hash; } stub_ctx;
+
+static void stub_mix(stub_ctx *c, const void *p, size_t n)           /* FNV-1a over what a generation call received */
+{
+    const unsigned char *b = p;
+    for (size_t i = 0; i < n; ++i) { c->hash ^= b[i]; c->hash *= 1099511628211ull; }
+}
+uint64_t stub_plan_hash(const gsgp_ctx *ctx) { return ((const stub_ctx *)ctx)->hash; }
 
 static double stub_fit(int32_t gen, int32_t k, int32_t which)      /* mirrored in the test */
 {
@@ -30,7 +37,7 @@ const char *gsgp_last_error(const gsgp_ctx *ctx) { (void)ctx; return "stub"; }
 int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
 {
     stub_ctx *c = calloc(1, sizeof *c);
-    c->P = cfg->population_size; c->n = cfg->nrow + cfg->nrow_test;
+    c->P = cfg->population_size; c->n = cfg->nrow + cfg->nrow_test; c->hash = 14695981039346656037ull;
     *out = (gsgp_ctx *)c;
     return 0;
 }
@@ -56,8 +63,12 @@ int gsgp_generation_compiled(gsgp_ctx *ctx, const gsgp_plan_entry *plan, const i
                              const int32_t *prog_desc, double *fit_out, double *fit_test_out, int32_t *index_best_out)
 {
     stub_ctx *c = (stub_ctx *)ctx;
-    (void)programs; (void)prog_off; (void)prog_desc;
     if (!plan || !tree_pool || pool_len < 0 || n_instructions < 0) return 1;
+    stub_mix(c, plan, sizeof(gsgp_plan_entry) * (size_t)c->P);
+    stub_mix(c, tree_pool, 4 * (size_t)pool_len);
+    stub_mix(c, programs, 8 * (size_t)n_instructions);
+    stub_mix(c, prog_off, 8 * (size_t)c->P);
+    stub_mix(c, prog_desc, 8 * (size_t)c->P);
     c->gen++;
     stub_fill(c, fit_out, fit_test_out, index_best_out);
     return 0;
