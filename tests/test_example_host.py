@@ -55,7 +55,7 @@ def test_example_host_host_half_with_a_stub_device(files, tmp_path):
     subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(stub), os.path.join(here, "stub_device.c")])
     gens, pop, seed = 40, 50, 1
     out = subprocess.run([exe, str(d / "train.txt"), str(d / "test.txt"), str(tmp_path), str(gens), str(pop), str(seed)],
-                         capture_output=True, text=True, env=dict(os.environ, LD_PRELOAD=str(stub)))
+                         capture_output=True, text=True, env=dict(os.environ, LD_PRELOAD=":".join(x for x in (os.environ.get("LD_PRELOAD"), str(stub)) if x)))
     assert out.returncode == 0, out.stderr
     host = HostDriver(population_size=pop, nvar=5, seed=seed)
     host.create_T_F(); host.initialize_population(0)

@@ -81,7 +81,7 @@ def test_shared_replay_loop_across_processes(tmp_path):
     stub = tmp_path / "libstub_device.so"
     subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(stub), os.path.join(HERE, "stub_device.c")])
     name = _name("replay")
-    env = dict(os.environ, LD_PRELOAD=str(stub), N_READERS="2")
+    env = dict(os.environ, LD_PRELOAD=":".join(x for x in (os.environ.get("LD_PRELOAD"), str(stub)) if x), N_READERS="2")
     P, G = 60, 30
     procs = {role: subprocess.Popen([sys.executable, WORKER, "replay", str(stub), role, name, str(P), str(G)],
                                     stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)

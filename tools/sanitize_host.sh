@@ -7,7 +7,7 @@ set -u
 cd "$(dirname "$0")/.."
 LIB=go_gsgp_b200/libgsgp_b200.so
 SRC="go_gsgp_b200/csrc/gsgp_b200.cu go_gsgp_b200/csrc/host.cpp"
-TESTS="tests/test_host_driver.py tests/test_ingest.py tests/test_program_builder.py tests/test_capi_symbols.py tests/test_golden.py tests/test_proto_dump.py tests/test_contributions.py"
+TESTS="tests/test_plan_channel.py tests/test_example_host.py tests/test_host_driver.py tests/test_ingest.py tests/test_program_builder.py tests/test_capi_symbols.py tests/test_golden.py tests/test_proto_dump.py tests/test_contributions.py"
 run() {   # $1 = -fsanitize flags, $2 = libraries to preload, $3 = linker libs, $4 = log
     nvcc -O1 -g -std=c++17 -shared -Xcompiler -fPIC,$1,-fno-omit-frame-pointer -gencode arch=compute_100a,code=sm_100a \
         -o $LIB $SRC -ldl -lz $3 || return 1
