@@ -6,6 +6,7 @@
 // draws are the ones main_cpu.go makes with the same -seed.
 //
 //   gsgp_b200_main <train> <test> <out_dir> [generations=10] [population=200] [seed=1] [linsc=0] [seed files...]
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -53,6 +54,7 @@ int main(int argc, char **argv)
     std::vector<double> sym((size_t)4 + nvar);
     gsgph_create_T_F(rng, &p, sym.data());                                      // :1371
     if (gsgp_set_constants(ctx, sym.data(), (int32_t)sym.size())) die(ctx, "gsgp_set_constants");
+    const auto start = std::chrono::steady_clock::now();                        // start = time.Now() :1374-1375
     if (n_seeds && gsgp_seed_semantic_files(ctx, 0, n_seeds, argv + 8)) die(ctx, "gsgp_seed_semantic_files");   // :1383-1388
 
     // initialize_population (:1400) + evaluate (:1402)
@@ -73,8 +75,10 @@ int main(int argc, char **argv)
     gsgph_contrib *contrib = gsgph_contrib_new(pop, n_seeds);
     FILE *f_contrib = fopen((out_dir + "/contributions.txt").c_str(), "w");
     if (!contrib || !f_contrib) { fprintf(stderr, "panic: cannot create the contributions file\n"); return 2; }
+    FILE *f_time = fopen((out_dir + "/executiontime.txt").c_str(), "w");        // :1413,1505: time.Since(start) per line
+    if (!f_time) { fprintf(stderr, "panic: cannot create the execution time file\n"); return 2; }
     std::vector<char> line(64);
-    auto write_best = [&] {                                                     // :1404-1411, :1494-1503
+    auto write_best = [&] {                                                     // :1404-1413, :1494-1505
         int64_t need = 0;
         if (gsgph_contrib_format(contrib, index_best, line.data(), (int64_t)line.size(), &need) == 3) {
             line.resize((size_t)need);
@@ -86,6 +90,9 @@ int main(int argc, char **argv)
         if (gsgp_get_semantic(ctx, index_best, sem.data())) die(ctx, "gsgp_get_semantic");
         gsgph_writer_semantic(s_train, sem.data(), nrow);
         gsgph_writer_semantic(s_test, sem.data() + nrow, nrow_test);
+        char dur[40];
+        gsgph_format_duration(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - start).count(), dur, sizeof dur);
+        fprintf(f_time, "%s\n", dur);
     };
     write_best();
 
@@ -109,6 +116,7 @@ int main(int argc, char **argv)
     if (gsgph_writer_close(f_train) | gsgph_writer_close(f_test) | gsgph_writer_close(s_train) | gsgph_writer_close(s_test)) {
         fprintf(stderr, "panic: cannot write the output files\n"); return 2;
     }
+    fclose(f_time);
     if (fclose(f_contrib) != 0) { fprintf(stderr, "panic: cannot write the contributions file\n"); return 2; }
     gsgph_contrib_free(contrib);
     gsgp_destroy(ctx);

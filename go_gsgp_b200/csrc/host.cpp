@@ -1876,4 +1876,54 @@ int gsgph_contrib_format(const gsgph_contrib *c, int32_t ind, char *out, int64_t
     return 0;
 }
 
+// time.Duration.String() (the executiontime lines, main_cpu.go:1413,1505: fmt.Fprintln(file, time.Since(start))):
+// below one second a single unit (ns, µs, ms) with the fraction's trailing zeros dropped, otherwise [h]m]s with up to nine
+// fractional digits of the seconds; "0s" for zero.
+int gsgph_format_duration(int64_t ns, char *out, int32_t cap)
+{
+    char buf[40];
+    int w = (int)sizeof buf;
+    uint64_t u = ns < 0 ? (uint64_t)0 - (uint64_t)ns : (uint64_t)ns;
+    auto frac = [&](int prec) {                        // fmtFrac: u / 10^prec, fraction without trailing zeros
+        bool print = false;
+        for (int i = 0; i < prec; ++i) {
+            const int digit = (int)(u % 10);
+            print = print || digit != 0;
+            if (print) buf[--w] = (char)('0' + digit);
+            u /= 10;
+        }
+        if (print) buf[--w] = '.';
+    };
+    auto integer = [&](uint64_t v) {                   // fmtInt
+        if (v == 0) { buf[--w] = '0'; return; }
+        while (v > 0) { buf[--w] = (char)('0' + v % 10); v /= 10; }
+    };
+    if (u < 1000000000ull) {
+        int prec;
+        buf[--w] = 's';
+        if (u == 0) { buf[--w] = '0'; prec = -1; }
+        else if (u < 1000ull) { prec = 0; buf[--w] = 'n'; }
+        else if (u < 1000000ull) { prec = 3; buf[--w] = (char)0xB5; buf[--w] = (char)0xC2; }   // U+00B5 micro sign
+        else { prec = 6; buf[--w] = 'm'; }
+        if (prec >= 0) { frac(prec); integer(u); }
+    } else {
+        buf[--w] = 's';
+        frac(9);                                       // u: whole seconds
+        integer(u % 60);
+        u /= 60;
+        if (u > 0) {
+            buf[--w] = 'm';
+            integer(u % 60);
+            u /= 60;
+            if (u > 0) { buf[--w] = 'h'; integer(u); }
+        }
+    }
+    if (ns < 0) buf[--w] = '-';
+    const int n = (int)sizeof buf - w;
+    if (!out || cap < n + 1) return -1;
+    memcpy(out, buf + w, (size_t)n);
+    out[n] = 0;
+    return n;
+}
+
 }  // extern "C"

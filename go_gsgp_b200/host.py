@@ -61,6 +61,7 @@ HOST_SIGNATURES = {
     "gsgph_writer_float": (C.c_int, [C.c_void_p, C.c_double]),
     "gsgph_writer_close": (C.c_int, [C.c_void_p]),
     "gsgph_gzip_member": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "gsgph_format_duration": (C.c_int, [C.c_int64, C.c_char_p, C.c_int32]),
     "gsgph_channel_create": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "gsgph_channel_attach": (C.c_void_p, [C.c_char_p, C.c_int32, C.c_int32]),
     "gsgph_channel_close": (None, [C.c_void_p]),
@@ -158,6 +159,13 @@ def compile_tree(tree, n_symbols):
     if rc:
         raise ValueError(f"malformed tree (gsgph_compile_tree rc={rc})")
     return out[0:2 * n.value:2].copy(), out[1:2 * n.value:2].copy(), need.value
+
+
+def format_duration(ns: int) -> str:
+    """time.Duration.String(): what fmt.Fprintln(executiontime, time.Since(start)) prints (main_cpu.go:1413,1505)"""
+    buf = C.create_string_buffer(40)
+    n = _lib().gsgph_format_duration(int(ns), buf, 40)
+    return buf.raw[:n].decode()
 
 
 def gzip_member(data: bytes) -> bytes:

@@ -149,6 +149,9 @@ int gsgph_parse_floats(const char *text, int64_t size, double *out, int64_t cap,
 
 /* Go fmt %v of a float64 (fitness / semantic output lines, main_cpu.go:123-126,1405-1409) */
 int gsgph_format_float(double v, char *buf, int32_t cap);
+/* time.Duration.String() of a nanosecond count: the executiontime lines (main_cpu.go:1413,1505, parsed by the harness's
+ * reporter.py:87-121), e.g. "1.234567ms", "2m3.5s", "1h0m0s".  Returns the length, -1 if cap (40 always suffices) is short. */
+int gsgph_format_duration(int64_t ns, char *out, int32_t cap);
 /* Semantic.String() (main_cpu.go:123-126): %v values joined by commas -- the best-of-generation semantic line
  * (:1499-1500).  Multi-threaded (n_threads <= 0: default); 25 bytes per value always suffice; non-zero if cap is short. */
 int gsgph_format_semantic(const double *v, int64_t n, char *out, int64_t cap, int64_t *len_out, int32_t n_threads);

@@ -7,8 +7,8 @@ Contents: BASELINE config 1 shape (5 vars x 1000/250 cases, pop 100), Philox str
 best-of-generation history, the full fitness vectors after the last generation, the first generation's decisions, and
 the hand-derived known answers of SURVEY Appendix B evaluated by the oracle.  Floats are stored as hex (exact).
 
-cfg1_go_seed1.json: the same shape under Go's own math/rand stream for `rand.Seed(1)` (the reference's default -seed,
-main_cpu.go:1367; the stream is pinned to real Go outputs, tools/gen_go_rng_cooked.py) with sequential sums
+cfg1_go_seed1.json: the same shape under Go's own math/rand stream for `rand.Seed(1)` (`-seed 1`; the flag's default is the clock,
+main_cpu.go:172,1367; the stream is pinned to real Go outputs, tools/gen_go_rng_cooked.py) with sequential sums
 (`-workers 1`): initial trees, first-generation plan and tree pool, best-of-generation history.  The product's host half
 (gsgph_rng / gsgph_initialize_population / gsgph_build_plan) is tested against it without the oracle in the loop."""
 import hashlib

@@ -77,6 +77,9 @@ def test_example_host_host_half_with_a_stub_device(files, tmp_path):
     assert (tmp_path / "fitnesstest.txt").read_text().split() == fte
     assert (tmp_path / "semantic_train.txt").read_text().split() == str_
     assert int(con[-1]) > 1                                    # crossovers happened: the best's lineage count grew
+    import re
+    times = (tmp_path / "executiontime.txt").read_text().split()   # Go Duration strings, one per line, increasing
+    assert len(times) == gens + 1 and all(re.fullmatch(r"(\d+h)?(\d+m)?\d+(\.\d+)?(ns|µs|ms|s)", t) for t in times)
     host.close()
 
 

@@ -86,7 +86,7 @@ def test_oracle_reproduces_go_stream_golden():
 
 def _host_driver_seed1():
     from go_gsgp_b200.host import HostDriver
-    return HostDriver(population_size=100, nvar=5, seed=1)       # the reference's default flags (main_cpu.go:157-169)
+    return HostDriver(population_size=100, nvar=5, seed=1)       # the reference's default flags (main_cpu.go:157-169) with -seed 1
 
 
 def test_host_half_reproduces_go_stream_golden():

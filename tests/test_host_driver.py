@@ -84,6 +84,19 @@ def test_format_float_matches_go_v():
     assert f(1e6) == "1e+06" and f(123456.0) == "123456" and f(0.5) == "0.5"
 
 
+def test_format_duration_matches_gos_duration_string():
+    """time.Duration.String() (executiontime lines, main_cpu.go:1413,1505): the vectors of Go's own time tests plus the
+    unit boundaries."""
+    from go_gsgp_b200.host import format_duration as f
+    US, MS, S, M, H = 10**3, 10**6, 10**9, 60 * 10**9, 3600 * 10**9
+    for want, ns in {"0s": 0, "1ns": 1, "1.1µs": 1100, "2.2ms": 2200 * US, "3.3s": 3300 * MS, "4m5s": 4 * M + 5 * S,
+                     "4m5.001s": 4 * M + 5001 * MS, "5h6m7.001s": 5 * H + 6 * M + 7001 * MS, "8m0.000000001s": 8 * M + 1,
+                     "2562047h47m16.854775807s": 2**63 - 1, "-2562047h47m16.854775808s": -2**63,
+                     "1h0m0s": H, "1m0s": M, "1s": S, "999ns": 999, "1µs": 1000, "999.999µs": MS - 1, "1ms": MS,
+                     "-1.5ms": -1500 * US, "1.000001ms": MS + 1, "999.999999ms": S - 1, "59.999999999s": 60 * S - 1}.items():
+        assert f(ns) == want, (ns, f(ns))
+
+
 def test_format_semantic_line():
     """Semantic.String() (main_cpu.go:123-126): %v values joined by commas; bulk path == per-value path == oracle."""
     from go_gsgp_b200.host import format_semantic, format_float

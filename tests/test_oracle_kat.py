@@ -66,7 +66,7 @@ def _go_rng_tool():
 
 def test_go_math_rand_known_answers():
     """ORC_RNG_ALFG is Go's math/rand (v1) seeded source, bit for bit: outputs of real Go programs with rand.Seed(1)
-    (what main_cpu.go:1367 runs with the default -seed) -- the Int63 / Intn(100) / Float64 sequences every Go program
+    (what main_cpu.go:1367 runs under `-seed 1`) -- the Int63 / Intn(100) / Float64 sequences every Go program
     that never seeds prints -- and with seed 42.  These pin the RNG half of the oracle to the real reference."""
     gen = _go_rng_tool()
     m63 = 2**63 - 1
