@@ -15,6 +15,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 WORKER = os.path.join(HERE, "channel_worker.py")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _needs_posix_shared_memory():
+    from go_gsgp_b200.host import PlanChannel
+    try:
+        PlanChannel.create(f"/gsgp_test_probe_{os.getpid()}", 1, 1, 1, 0).close()
+    except OSError:
+        pytest.skip("no POSIX shared memory in this environment (shm_open failed)")
+
+
 def _name(tag):
     return f"/gsgp_test_{tag}_{os.getpid()}"
 
