@@ -84,3 +84,35 @@ def test_host_header_symbols_are_exported_and_bound(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/gsgp_host.h but not exported"
     assert set(names) == set(host.HOST_SIGNATURES), set(names) ^ set(host.HOST_SIGNATURES)
+
+
+def test_headers_are_plain_c_and_link_from_c(tmp_path):
+    """cgo compiles the preamble as C: both headers must be valid C99 (no C++-isms), and a C program must link against
+    the library and call it (here: ABI version, config defaults, two host-side formatters -- nothing that needs a GPU)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "cabi.c"
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "gsgp_b200.h"
+#include "gsgp_host.h"
+int main(void)
+{
+    gsgp_config cfg;
+    char buf[64];
+    gsgp_config_defaults(&cfg);
+    if (gsgp_abi_version() != 1 || sizeof(gsgp_plan_entry) != 40) return 1;
+    if (gsgph_format_duration(1500000, buf, (int32_t)sizeof buf) < 0 || strcmp(buf, "1.5ms") != 0) return 2;
+    if (gsgph_format_float(1e6, buf, (int32_t)sizeof buf) != 5 || strcmp(buf, "1e+06") != 0) return 3;
+    printf("%d %s\\n", (int)cfg.tournament_size, buf);
+    return 0;
+}
+''')
+    exe = tmp_path / "cabi"
+    libdir = os.path.join(root, "go_gsgp_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           "-o", str(exe), str(src), "-L" + libdir, "-lgsgp_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stderr)
+    assert out.stdout.split() == ["4", "1e+06"]                # main_cpu.go:161 tournament_size default, %v of 1e6
