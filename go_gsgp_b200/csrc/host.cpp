@@ -1713,6 +1713,7 @@ int gsgph_proto_add_individual(gsgph_proto *d, int32_t op, double fitness_train,
         if (rt_semantic_test && rt_semantic_test[t]) gsgph_proto::packed_f64(d->rt, 3, rt_semantic_test[t], nrow_test);
         gsgph_proto::bytes(o, 7, d->rt.data(), d->rt.size());
     }
+    if (o.size() + d->pop.size() + d->evo.size() > (size_t)0x7fffffff - 64) return 4;   // protobuf's 2 GB limit (proto.Marshal fails too)
     gsgph_proto::bytes(d->pop, 2, o.data(), o.size());
     return 0;
 }

@@ -179,7 +179,8 @@ int gsgph_gzip_member(const char *src, int64_t n, char *out, int64_t cap, int64_
  *   contrib            contrib[k].AsBytes() of the host's bookkeeping (may be NULL / 0)
  *   rt_*               the operator's random trees {rt, sem_rt_train, sem_rt_test} (:1456-1466): n_rt = 0, 1 or 2;
  *                      rt_semantic_train[t] has nrow values, rt_semantic_test[t] nrow_test (either array may be NULL)
- * All pointers are read during the call only.  Non-zero: bad arguments / wrong call order; gsgph_proto_write 2: I/O. */
+ * All pointers are read during the call only.  Non-zero: bad arguments / wrong call order; gsgph_proto_add_individual 4:
+ * the dump would pass protobuf's 2 GB message limit (where the reference's proto.Marshal fails); gsgph_proto_write 2: I/O. */
 typedef struct gsgph_proto gsgph_proto;
 gsgph_proto *gsgph_proto_new(void);                                            /* new(pb.Evolution) :1419 */
 void gsgph_proto_free(gsgph_proto *d);
