@@ -1771,7 +1771,9 @@ struct gsgph_contrib {
         for (int32_t k = k0; k < k1; ++k) {
             const gsgp_plan_entry &e = plan[k];
             uint64_t *d = &nxt[(size_t)k * row];
-            const uint64_t *a = &cur[(size_t)e.p1 * row];
+            // the elite keeps its own vector whatever the operator (:847,:857 with i == old_i, :909); device-mode plans
+            // (gsgp_get_plan) do not define p1 for it
+            const uint64_t *a = &cur[(size_t)(e.elite ? k : e.p1) * row];
             if (e.op == GSGP_OP_XO && !e.elite) {                             // merge_contribs :869-873,885
                 const uint64_t *b = &cur[(size_t)e.p2 * row];
                 if (W == 1) {
@@ -1817,8 +1819,9 @@ int gsgph_contrib_apply(gsgph_contrib *c, const gsgp_plan_entry *plan, int32_t n
     if (!c || !plan) return 1;
     for (int32_t k = 0; k < c->P; ++k) {
         const gsgp_plan_entry &e = plan[k];
+        if (e.elite) continue;
         if (e.p1 < 0 || e.p1 >= c->P) return 2;
-        if (e.op == GSGP_OP_XO && !e.elite && (e.p2 < 0 || e.p2 >= c->P)) return 2;
+        if (e.op == GSGP_OP_XO && (e.p2 < 0 || e.p2 >= c->P)) return 2;
     }
     if (n_threads <= 0) n_threads = (int32_t)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
     if ((int64_t)c->P * c->M * c->W < (1 << 16)) n_threads = 1;               // small tables: not worth the threads

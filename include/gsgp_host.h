@@ -202,7 +202,8 @@ int gsgph_proto_write(const gsgph_proto *d, const char *path);                 /
  * arrays that widen on demand, so a generation of config 3 (pop 2,000 x 501 models) is one streaming pass.
  *   gsgph_contrib_new     init_tables + the initial slots (:1272-1283,1390-1397)
  *   gsgph_contrib_apply   one generation from its plan (op / elite / p1 / p2), then the swap of update_tables (:1196);
- *                         2: a parent index out of range
+ *                         an elite entry keeps its own vector (its p1 / p2 are not read: gsgp_get_plan leaves them
+ *                         undefined in device mode); 2: a parent index out of range
  *   gsgph_contrib_format  Contribution.String() of one individual (:141-146, the line written at :1411,1503 and the
  *                         bytes of pb.Individual.contrib :1430,1479); 3: cap too small (len_out = needed) */
 typedef struct gsgph_contrib gsgph_contrib;

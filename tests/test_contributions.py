@@ -14,10 +14,12 @@ def _model_new(P, n_seeds):                                    # init_tables + :
 
 def _model_apply(cur, plan):
     new = []
-    for e in plan:
-        if e["op"] == capi.OP_XO and not e["elite"]:           # merge_contribs :885
+    for k, e in enumerate(plan):
+        if e["elite"]:                                         # the elite keeps its own vector (:847,857,909)
+            new.append(list(cur[k]))
+        elif e["op"] == capi.OP_XO:                            # merge_contribs :885
             new.append([a + b for a, b in zip(cur[e["p1"]], cur[e["p2"]])])
-        else:                                                  # copy_contrib :857,909
+        else:                                                  # copy_contrib :857
             new.append(list(cur[e["p1"]]))
     return new
 
@@ -29,7 +31,7 @@ def _random_plan(rng, P, best, p_xo=0.6, p_mut=0.3):
     plan["p1"], plan["p2"] = rng.integers(0, P, P), rng.integers(0, P, P)
     plan["p2"][plan["op"] != capi.OP_XO] = -1
     plan["elite"][best] = 1
-    plan["p1"][best], plan["p2"][best] = best, -1
+    plan["p1"][best], plan["p2"][best] = (best, -1) if rng.random() < 0.5 else (-7, 10**6)   # device-mode plans leave them undefined
     return plan
 
 
