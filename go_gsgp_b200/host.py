@@ -358,20 +358,22 @@ class ProtoDump:
             self.add_individual(capi.OP_INIT, fit[k], fit_test[k], semantics[k], contribs[k] if contribs else b"")
         self.end_population()
 
-    def add_generation(self, generation, plan, pool, fit_new, fit_test_new, semantics_new, tree_semantic, contribs=None):
+    def add_generation(self, generation, plan, pool, fit_new, fit_test_new, semantics_new, tree_semantic, contribs=None, tree=None):
         """one generation's loop (:1441-1488) from the plan that produced it.  tree_semantic(k, which) -> the semantic of
         individual k's random tree (Engine.get_tree_semantic with GSGP_FLAG_KEEP_TREE_SEMANTICS).  The elite creates no
         tree, so -- as in the reference, where rt1 / rt2 are globals -- its entry repeats the previous individual's.
         contribs: Contribution.String() bytes per individual; the reference passes contrib[k] of the generation being
-        replaced (:1479, before update_tables swaps the tables)."""
+        replaced (:1479, before update_tables swaps the tables).  tree(k, which) -> the tree array, instead of `pool`
+        (device mode keeps the trees on the device: Engine.get_tree)."""
         self.begin_population(generation)
         for k in range(len(plan)):
             e = plan[k]
             op = int(e["op"])
             if op in (capi.OP_XO, capi.OP_MUT) and not e["elite"]:
-                self._rt[0] = (pool[e["tree0_off"]: e["tree0_off"] + e["tree0_len"]].copy(), tree_semantic(k, 0))
+                arr = tree if tree is not None else (lambda k_, w_: pool[e[f"tree{w_}_off"]: e[f"tree{w_}_off"] + e[f"tree{w_}_len"]].copy())
+                self._rt[0] = (arr(k, 0), tree_semantic(k, 0))
                 if op == capi.OP_MUT:
-                    self._rt[1] = (pool[e["tree1_off"]: e["tree1_off"] + e["tree1_len"]].copy(), tree_semantic(k, 1))
+                    self._rt[1] = (arr(k, 1), tree_semantic(k, 1))
             trees = [r if r is not None else (None, None) for r in self._rt[: {capi.OP_XO: 1, capi.OP_MUT: 2}.get(op, 0)]]
             self.add_individual(op, fit_new[k], fit_test_new[k], semantics_new[k], contribs[k] if contribs else b"", trees)
         self.end_population()

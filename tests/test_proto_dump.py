@@ -94,17 +94,21 @@ def test_dump_of_a_run_reads_back(tmp_path):
     o.keep_tree_semantics(True)
     d = ProtoDump(nrow, 90 - nrow)
     d.add_initial_population(o.fit(), o.fit_test(), o.semantics())
+    d2 = ProtoDump(nrow, 90 - nrow)                            # the same dump with the trees fetched one by one (device mode)
+    d2.add_initial_population(o.fit(), o.fit_test(), o.semantics())
     record = []
     for gen in range(1, 4):
         o.generation()
         plan, pool = o.last_plan().copy(), o.last_tree_pool().copy()
         d.add_generation(gen, plan, pool, o.fit(), o.fit_test(), o.semantics(), o.last_tree_semantic)
+        d2.add_generation(gen, plan, None, o.fit(), o.fit_test(), o.semantics(), o.last_tree_semantic,
+                          tree=lambda k, w: pool[plan[f"tree{w}_off"][k]: plan[f"tree{w}_off"][k] + plan[f"tree{w}_len"][k]])
         record.append((plan, pool, o.fit().copy(), o.semantics().copy(),
                        {(k, w): o.last_tree_semantic(k, w).copy() for k in range(P) for w in (0, 1)
                         if plan[("tree0_len", "tree1_len")[w]][k] > 0 and not plan["elite"][k]}))
     path = tmp_path / "dump.pb"
     d.write(path)
-    assert path.read_bytes() == d.tobytes()
+    assert path.read_bytes() == d.tobytes() == d2.tobytes()
     evo = pb["Evolution"].FromString(path.read_bytes())
     assert [p.generation for p in evo.generations] == [0, 1, 2, 3]
     assert all(i.op == 0 and not i.rt for i in evo.generations[0].individuals)
