@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgsgp_b200.so")
 SOURCES = [os.path.join(CSRC, "gsgp_b200.cu"), os.path.join(CSRC, "host.cpp")]
-DEPS = [os.path.join(CSRC, f) for f in ("gsgp_b200.cu", "kernels.cuh", "interp_div.inc.h", "go_rng_cooked.inc.h", "program.hpp", "rng.cuh", "trees.hpp", "host.cpp")] + [
+DEPS = [os.path.join(CSRC, f) for f in ("gsgp_b200.cu", "kernels.cuh", "interp_div.inc.h", "interp_body.inc.h", "go_rng_cooked.inc.h", "program.hpp", "rng.cuh", "trees.hpp", "host.cpp")] + [
     os.path.join(os.path.dirname(HERE), "include", f) for f in ("gsgp_b200.h", "gsgp_host.h")]
 
 

@@ -208,6 +208,7 @@ struct gsgp_ctx {
     // cases whose old values every individual has already consumed.  Memory = (1 + shift/n_pad) x the store, no copies.
     bool single_store = false;
     int32_t gen_warps = kGenWarpsDefault;                         // warps per gen_kernel block
+    int32_t gen_nsub = 0;                                         // 0: gen_kernel (parents by TMA); 1, 2: gen2_kernel with that many 256-case tiles per block
     int32_t shift_tiles = 0;                                  // case tiles (256 cases) per block
     int64_t pitch = 0;                                        // row pitch of the store in doubles
     double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
@@ -385,48 +386,77 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     return 0;
 }
 
-// fused pipeline: shared memory of one gen_kernel block for `ipg` individuals per group
-size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps)
+// fused pipeline: shared memory of one gen_kernel / gen2_kernel block for `ipg` individuals per group
+size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps, int32_t nsub)
 {
     const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
-    const size_t per_warp = ((size_t)(levels + 2) * kPass + 2 * 2 * kGenProgSmem) * sizeof(double);
-    return (ncol + 1) * kPass * sizeof(double) + per_warp * warps + (size_t)ipg * sizeof(GenSlot) +
-           (1 + warps) * sizeof(uint64_t) + 16;
+    if (nsub == 0) {
+        const size_t per_warp = ((size_t)(levels + 2) * kPass + 2 * 2 * kGenProgSmem) * sizeof(double);
+        return (ncol + 1) * kPass * sizeof(double) + per_warp * warps + (size_t)ipg * sizeof(GenSlot) +
+               (1 + warps) * sizeof(uint64_t) + 16;
+    }
+    const size_t blk = (size_t)kPass * nsub;
+    const size_t per_warp = ((size_t)levels * blk + 2 * 2 * kGenProgSmem) * sizeof(double);
+    return (ncol + 1) * blk * sizeof(double) + per_warp * warps + (size_t)ipg * sizeof(GenSlot) + sizeof(uint64_t) + 16;
+}
+
+// the instantiated (warps, tiles per block) shapes of gen2_kernel
+#define GSGP_GEN2_SHAPES(X) X(12, 2) X(16, 1) X(8, 2) X(10, 2) X(20, 1) X(24, 1)
+
+template <int MEASURE>
+int launch_gen_kernel(gsgp_ctx *c, dim3 grid, size_t smem, const GenArgs &a)
+{
+    if (c->gen_nsub == 0) {
+        gen_kernel<MEASURE, kGenWarpsDefault><<<grid, kGenWarpsDefault * 32, smem, c->stream>>>(a);
+        return 0;
+    }
+#define GSGP_LAUNCH(W, N) if (c->gen_warps == W && c->gen_nsub == N) { gen2_kernel<MEASURE, W, N><<<grid, W * 32, smem, c->stream>>>(a); return 0; }
+    GSGP_GEN2_SHAPES(GSGP_LAUNCH)
+#undef GSGP_LAUNCH
+    return fail(c, "gen2_kernel: shape %d warps x %d tiles is not instantiated", c->gen_warps, c->gen_nsub);
 }
 
 template <int MEASURE>
-void launch_gen_kernel(gsgp_ctx *c, dim3 grid, size_t smem, const GenArgs &a)
+cudaError_t gen_kernels_allow_smem(int bytes)
 {
-    gen_kernel<MEASURE, kGenWarpsDefault><<<grid, kGenWarpsDefault * 32, smem, c->stream>>>(a);
+    cudaError_t e = cudaFuncSetAttribute(gen_kernel<MEASURE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#define GSGP_ATTR(W, N) if (e == cudaSuccess) e = cudaFuncSetAttribute(gen2_kernel<MEASURE, W, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    GSGP_GEN2_SHAPES(GSGP_ATTR)
+#undef GSGP_ATTR
+    return e;
 }
 
 int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const double *sem_old, double *sem_new,
                      int32_t tile_begin, int32_t tile_count, double bytes)
 {
     if (nk <= 0 || tile_count <= 0) return 0;
-    const int32_t n_tiles = tile_count;
+    const int32_t per_block = std::max(1, c->gen_nsub);               // 256-case tiles per block
+    const int32_t n_blocks = (tile_count + per_block - 1) / per_block;
     static const int32_t waves = getenv("GSGP_GEN_WAVES") ? std::max(1, atoi(getenv("GSGP_GEN_WAVES"))) : 8;
     const int32_t target = c->sm_count * waves;
-    int32_t groups = std::max(1, (target + n_tiles - 1) / n_tiles);
-    groups = std::min(groups, std::max(1, (nk + kGenWarpsDefault - 1) / kGenWarpsDefault));   // >= one individual per warp
+    int32_t groups = std::max(1, (target + n_blocks - 1) / n_blocks);
+    groups = std::min(groups, std::max(1, (nk + c->gen_warps - 1) / c->gen_warps));   // >= one individual per warp
     int32_t ipg = (nk + groups - 1) / groups;
-    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
+    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_nsub) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
     groups = (nk + ipg - 1) / ipg;
     if (groups > 65535) return fail(c, "population chunk too large for one launch");
     GenArgs a{};
     a.plan = c->dplan; a.prog_pool = c->ds[c->dcur].prog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->ds[c->dcur].prog_desc;
     a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
-    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin; a.partial = c->dpartial;
+    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin; a.tile_end = tile_begin + tile_count;
+    a.partial = c->dpartial;
     a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = c->n_tiles_gen; a.smem_levels = c->gen_levels; a.L = c->L;
-    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps);
-    dim3 grid(n_tiles, groups);
+    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_nsub);
+    dim3 grid(n_blocks, groups);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
+    int rc;
     switch (c->linsc ? GSGP_SUMO : c->cfg.error_measure) {
-    case GSGP_SUMO: launch_gen_kernel<GSGP_SUMO>(c, grid, smem, a); break;
-    case GSGP_MAE: launch_gen_kernel<GSGP_MAE>(c, grid, smem, a); break;
-    case GSGP_MRE: launch_gen_kernel<GSGP_MRE>(c, grid, smem, a); break;
-    default:       launch_gen_kernel<GSGP_MSE>(c, grid, smem, a); break;
+    case GSGP_SUMO: rc = launch_gen_kernel<GSGP_SUMO>(c, grid, smem, a); break;
+    case GSGP_MAE: rc = launch_gen_kernel<GSGP_MAE>(c, grid, smem, a); break;
+    case GSGP_MRE: rc = launch_gen_kernel<GSGP_MRE>(c, grid, smem, a); break;
+    default:       rc = launch_gen_kernel<GSGP_MSE>(c, grid, smem, a); break;
     }
+    if (rc) return rc;
     CU(c, cudaGetLastError());
     return 0;
 }
@@ -893,10 +923,10 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         const int kMaxSmem = 227 * 1024;
         CUC(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CUC(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MSE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MAE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_MRE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CUC(cudaFuncSetAttribute(gen_kernel<GSGP_SUMO, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CUC(gen_kernels_allow_smem<GSGP_MSE>(kMaxSmem));
+        CUC(gen_kernels_allow_smem<GSGP_MAE>(kMaxSmem));
+        CUC(gen_kernels_allow_smem<GSGP_MRE>(kMaxSmem));
+        CUC(gen_kernels_allow_smem<GSGP_SUMO>(kMaxSmem));
         CUC(cudaFuncSetAttribute(plan_draw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         c->linsc = (cfg->flags & GSGP_FLAG_LINEAR_SCALING) != 0;
         c->keep_run = (cfg->flags & GSGP_FLAG_KEEP_RUN_HISTORY) != 0;
@@ -904,8 +934,28 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         // do not fit shared memory, the caller wants R kept (proto dump), or GSGP_PIPELINE=unfused
         const char *pl = getenv("GSGP_PIPELINE");
         c->gen_levels = 2;
-        c->fused = !(cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) && !(pl && strcmp(pl, "unfused") == 0) &&
-                   gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps) <= (size_t)kMaxSmem;
+        // shape of the fused kernel: the first that fits the dataset's columns into shared memory -- two 256-case tiles
+        // per block (16 cases per lane) x 12 warps, one tile x 16 warps, then gen_kernel (parents staged by TMA).
+        // GSGP_GEN_KERNEL = "v1" | "<warps>x<tiles>" picks one (A/B runs).
+        const int shapes[][2] = {{12, 2}, {16, 1}, {kGenWarpsDefault, 0}};
+        int pick_w = 0, pick_n = -1;
+        if (const char *e = getenv("GSGP_GEN_KERNEL")) {
+            int w = 0, n = 0;
+            if (strcmp(e, "v1") == 0) { pick_w = kGenWarpsDefault; pick_n = 0; }
+            else if (sscanf(e, "%dx%d", &w, &n) == 2) { pick_w = w; pick_n = n; }
+        }
+        bool fits = false;
+        if (pick_n >= 0) {
+            c->gen_warps = pick_w; c->gen_nsub = pick_n;
+            fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps, c->gen_nsub) <= (size_t)kMaxSmem;
+        } else {
+            for (const auto &sh : shapes) {
+                c->gen_warps = sh[0]; c->gen_nsub = sh[1];
+                fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps, c->gen_nsub) <= (size_t)kMaxSmem;
+                if (fits) break;
+            }
+        }
+        c->fused = !(cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) && !(pl && strcmp(pl, "unfused") == 0) && fits;
     }
     // +256 doubles of slack: the unstaged multi-pair path may read (never use) past the last tile
     CUC(cudaMalloc((void **)&c->dX, sizeof(double) * (row * cfg->nvar + 256)));
