@@ -207,8 +207,8 @@ struct gsgp_ctx {
     // (alternately right and left), one block of `shift` cases per launch in the order that only ever overwrites
     // cases whose old values every individual has already consumed.  Memory = (1 + shift/n_pad) x the store, no copies.
     bool single_store = false;
-    int32_t gen_warps = kGenWarpsDefault;                         // warps per gen_kernel block
-    int32_t gen_nsub = 0;                                         // 0: gen_kernel (parents by TMA); 1, 2: gen2_kernel with that many 256-case tiles per block
+    bool gen_tmem = false;                                        // gen_kernel keeps the X tile in tensor memory (tcgen05.ld operand fetches)
+    int32_t gen_warps = 16;                         // warps per gen_kernel block
     int32_t shift_tiles = 0;                                  // case tiles (256 cases) per block
     int64_t pitch = 0;                                        // row pitch of the store in doubles
     double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
@@ -386,43 +386,39 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     return 0;
 }
 
-// fused pipeline: shared memory of one gen_kernel / gen2_kernel block for `ipg` individuals per group
-size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps, int32_t nsub)
+// fused pipeline: shared memory of one gen_kernel block for `ipg` individuals per group (tmem: the X tile lives in tensor memory)
+size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps, bool tmem)
 {
     const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
-    if (nsub == 0) {
-        const size_t per_warp = ((size_t)(levels + 2) * kPass + 2 * 2 * kGenProgSmem) * sizeof(double);
-        return (ncol + 1) * kPass * sizeof(double) + per_warp * warps + (size_t)ipg * sizeof(GenSlot) +
-               (1 + warps) * sizeof(uint64_t) + 16;
-    }
-    const size_t blk = (size_t)kPass * nsub;
-    const size_t per_warp = ((size_t)levels * blk + 2 * 2 * kGenProgSmem) * sizeof(double);
-    return (ncol + 1) * blk * sizeof(double) + per_warp * warps + (size_t)ipg * sizeof(GenSlot) + sizeof(uint64_t) + 16;
+    const size_t per_warp = ((size_t)levels * kPass + 2 * 2 * kGenProgSlots) * sizeof(double);
+    return (tmem ? 0 : (ncol + 1) * kPass * sizeof(double)) + per_warp * warps + (size_t)ipg * (sizeof(GenSlot) + 8) + sizeof(uint64_t) + 16 + 4 * kCostBuckets;
 }
 
-// the instantiated (warps, tiles per block) shapes of gen2_kernel
-#define GSGP_GEN2_SHAPES(X) X(12, 2) X(16, 1) X(8, 2) X(10, 2) X(20, 1) X(24, 1)
+// the instantiated block sizes of gen_kernel (warps per block, one block per SM)
+#define GSGP_GEN_WARPS(X) X(16) X(20) X(24) X(28)
 
 template <int MEASURE>
 int launch_gen_kernel(gsgp_ctx *c, dim3 grid, size_t smem, const GenArgs &a)
 {
-    if (c->gen_nsub == 0) {
-        gen_kernel<MEASURE, kGenWarpsDefault><<<grid, kGenWarpsDefault * 32, smem, c->stream>>>(a);
-        return 0;
-    }
-#define GSGP_LAUNCH(W, N) if (c->gen_warps == W && c->gen_nsub == N) { gen2_kernel<MEASURE, W, N><<<grid, W * 32, smem, c->stream>>>(a); return 0; }
-    GSGP_GEN2_SHAPES(GSGP_LAUNCH)
+#define GSGP_LAUNCH(W) if (c->gen_warps == W) { \
+        if (c->gen_tmem) gen_kernel<MEASURE, W, true><<<grid, W * 32, smem, c->stream>>>(a); \
+        else gen_kernel<MEASURE, W, false><<<grid, W * 32, smem, c->stream>>>(a); \
+        return 0; }
+    GSGP_GEN_WARPS(GSGP_LAUNCH)
 #undef GSGP_LAUNCH
-    return fail(c, "gen2_kernel: shape %d warps x %d tiles is not instantiated", c->gen_warps, c->gen_nsub);
+    if (c->gen_warps == 12 && !c->gen_tmem) { gen_kernel<MEASURE, 12, false><<<grid, 12 * 32, smem, c->stream>>>(a); return 0; }
+    return fail(c, "gen_kernel: %d warps per block is not instantiated", c->gen_warps);
 }
 
 template <int MEASURE>
 cudaError_t gen_kernels_allow_smem(int bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(gen_kernel<MEASURE, kGenWarpsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-#define GSGP_ATTR(W, N) if (e == cudaSuccess) e = cudaFuncSetAttribute(gen2_kernel<MEASURE, W, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    GSGP_GEN2_SHAPES(GSGP_ATTR)
+    cudaError_t e = cudaSuccess;
+#define GSGP_ATTR(W) if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+                     if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    GSGP_GEN_WARPS(GSGP_ATTR)
 #undef GSGP_ATTR
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 
@@ -430,23 +426,23 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
                      int32_t tile_begin, int32_t tile_count, double bytes)
 {
     if (nk <= 0 || tile_count <= 0) return 0;
-    const int32_t per_block = std::max(1, c->gen_nsub);               // 256-case tiles per block
-    const int32_t n_blocks = (tile_count + per_block - 1) / per_block;
+    const int32_t n_blocks = tile_count;
     static const int32_t waves = getenv("GSGP_GEN_WAVES") ? std::max(1, atoi(getenv("GSGP_GEN_WAVES"))) : 8;
     const int32_t target = c->sm_count * waves;
     int32_t groups = std::max(1, (target + n_blocks - 1) / n_blocks);
     groups = std::min(groups, std::max(1, (nk + c->gen_warps - 1) / c->gen_warps));   // >= one individual per warp
     int32_t ipg = (nk + groups - 1) / groups;
-    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_nsub) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
+    const size_t smem_cap = c->gen_warps <= 12 ? (size_t)112 * 1024 : (size_t)227 * 1024;    // 12 warps: two blocks per SM
+    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_tmem) > smem_cap) ipg = (ipg + 1) / 2;
     groups = (nk + ipg - 1) / ipg;
     if (groups > 65535) return fail(c, "population chunk too large for one launch");
     GenArgs a{};
     a.plan = c->dplan; a.prog_pool = c->ds[c->dcur].prog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->ds[c->dcur].prog_desc;
     a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
-    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin; a.tile_end = tile_begin + tile_count;
+    a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin;
     a.partial = c->dpartial;
     a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = c->n_tiles_gen; a.smem_levels = c->gen_levels; a.L = c->L;
-    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_nsub);
+    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_tmem);
     dim3 grid(n_blocks, groups);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
     int rc;
@@ -934,26 +930,20 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         // do not fit shared memory, the caller wants R kept (proto dump), or GSGP_PIPELINE=unfused
         const char *pl = getenv("GSGP_PIPELINE");
         c->gen_levels = 2;
-        // shape of the fused kernel: the first that fits the dataset's columns into shared memory -- two 256-case tiles
-        // per block (16 cases per lane) x 12 warps, one tile x 16 warps, then gen_kernel (parents staged by TMA).
-        // GSGP_GEN_KERNEL = "v1" | "<warps>x<tiles>" picks one (A/B runs).
-        const int shapes[][2] = {{12, 2}, {16, 1}, {kGenWarpsDefault, 0}};
-        int pick_w = 0, pick_n = -1;
-        if (const char *e = getenv("GSGP_GEN_KERNEL")) {
-            int w = 0, n = 0;
-            if (strcmp(e, "v1") == 0) { pick_w = kGenWarpsDefault; pick_n = 0; }
-            else if (sscanf(e, "%dx%d", &w, &n) == 2) { pick_w = w; pick_n = n; }
-        }
+        // warps per gen_kernel block (one block per SM): the kernel is bound by its warps' issue rate, so as many as the
+        // register file carries without spills; fewer when the dataset's columns leave less shared memory.
+        // GSGP_GEN_WARPS picks one of the instantiated sizes (A/B runs).
+        // The X tile lives in tensor memory when its columns (+ constants + the targets) fit the SM's 512 TMEM columns,
+        // 16 each; wider datasets stage it in shared memory.  GSGP_GEN_OPERANDS=smem forces the latter (A/B runs).
         bool fits = false;
-        if (pick_n >= 0) {
-            c->gen_warps = pick_w; c->gen_nsub = pick_n;
-            fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps, c->gen_nsub) <= (size_t)kMaxSmem;
-        } else {
-            for (const auto &sh : shapes) {
-                c->gen_warps = sh[0]; c->gen_nsub = sh[1];
-                fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps, c->gen_nsub) <= (size_t)kMaxSmem;
-                if (fits) break;
-            }
+        const int env_w = getenv("GSGP_GEN_WARPS") ? atoi(getenv("GSGP_GEN_WARPS")) : 0;
+        const char *opnd = getenv("GSGP_GEN_OPERANDS");
+        c->gen_tmem = cfg->nvar + cfg->num_constants + 1 <= kTmemMaxOperands && !(opnd && strcmp(opnd, "smem") == 0);
+        for (int w : {env_w, 24, 20, 16}) {
+            if (w <= 0) continue;
+            c->gen_warps = w;
+            fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps, c->gen_tmem) <= (size_t)kMaxSmem;
+            if (fits || w == env_w) break;
         }
         c->fused = !(cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) && !(pl && strcmp(pl, "unfused") == 0) && fits;
     }

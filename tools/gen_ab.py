@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""A/B timing of the fused generation kernel's shapes (GSGP_GEN_KERNEL) in one process.
+"""A/B timing of the fused generation kernel's block sizes (GSGP_GEN_WARPS) in one process.
 
-    python tools/gen_ab.py [--workload cfg2] [--steps 30] [--variants v1,16x1,12x2] [--pop N]
+    python tools/gen_ab.py [--workload cfg2] [--steps 30] [--variants 16,20,24] [--pop N]
 
 For every variant: a fresh device-mode engine on the same synthetic workload, W warm-up generations, K generations
 timed with the library's own per-launch CUDA events (gsgp_profile_read: the generation kernel's launches only) and
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--variants", default="v1,16x1,12x2,8x2,10x2,20x1,24x1")
+    ap.add_argument("--variants", default="16,20,24,28")
     ap.add_argument("--pop", type=int, default=0)
     ap.add_argument("--cases", type=int, default=0)
     args = ap.parse_args()
@@ -51,7 +51,7 @@ def main():
     init_trees = host.initialize_population(0)
     ref_fit = None
     for var in args.variants.split(","):
-        os.environ["GSGP_GEN_KERNEL"] = var
+        os.environ["GSGP_GEN_WARPS"] = var
         os.environ["GSGP_PIPELINE"] = "fused"
         e = Engine(rng_mode=capi.RNG_DEVICE_PHILOX, population_size=P, nvar=V, nrow=nrow, nrow_test=n - nrow,
                    max_depth_creation=w["depth"], error_measure=capi.RMSE, p_crossover=w["p_xo"], p_mutation=w["p_mut"],
