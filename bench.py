@@ -54,6 +54,11 @@ WORKLOADS = {
     # two buffers do not fit 180 GB, so the library switches to the single-buffer store (case-block scratch)
     "cfg5full": dict(cfg_id=5, nvar=20, cases_per_gpu=1_250_000, pop=10_000, depth=6, p_xo=0.6, p_mut=0.3,
                      desc="synthetic 20 vars x 1.25M cases per GPU (10M at 8 GPUs), pop 10,000, single-buffer store"),
+    # BASELINE.json configs[4], strong scaling (north_star: ">= 6x at 8 GPUs on the 10M-case config"): 10M cases in TOTAL at
+    # every GPU count, with a population that fits one GPU (pop 1000 x 10M cases = 80 GB of semantics: the single-buffer
+    # store at N = 1, two buffers from N = 2 on).  --scaling strong is implied.
+    "cfg5s": dict(cfg_id=5, nvar=20, cases_per_gpu=10_000_000, pop=1000, depth=6, p_xo=0.6, p_mut=0.3, strong=True,
+                  desc="synthetic 20 vars x 10M cases in total (strong scaling: 10M / N per GPU), pop 1000"),
 }
 
 
@@ -112,6 +117,21 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ref_arm_pop(w, n_cases):
+    """population subsample of the reference (CPU) arm: ~2e7 updates per generation, at the full case count"""
+    return max(8, min(w["pop"], int(2e7 // n_cases)))
+
+
+def config_dict(workload, w, world, scaling):
+    """`config` of the JSON line: the same dict in both arms (the driver compares them)"""
+    n_global = w["cases_per_gpu"] if scaling == "strong" else w["cases_per_gpu"] * world
+    n_local = n_global // world if scaling == "strong" else w["cases_per_gpu"]
+    return {"workload": f"{workload}: {w['desc']}", "global_cases": n_global, "pop": w["pop"], "scaling": scaling,
+            "l2": "inputs larger than L2 (semantic store %.2f GB per buffer per GPU)" % (w["pop"] * n_local * 8 / 1e9),
+            "reference_arm": "--impl reference runs the CPU restatement of main_cpu.go at %d cases with a population subsample of "
+                             "%d and reports updates/s (its cost is linear in the population)" % (n_local, ref_arm_pop(w, n_local))}
+
+
 # ------------------------------------------------------------------------------------------------
 def oracle_arm(w, n_cases, pop, gens, warm, workers):
     """Times the C restatement of main_cpu.go (the oracle) on the host cores: `gens` generations
@@ -142,18 +162,20 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     workers = os.cpu_count() or 1
-    n_cases = w["cases_per_gpu"]
-    pop = max(8, min(w["pop"], int(2e7 // n_cases)))           # bounded sample: ~2e7 updates per step
+    world = max(1, args.gpus)
+    scaling = args.scaling or ("strong" if w.get("strong") else "weak")
+    n_cases = w["cases_per_gpu"] // world if scaling == "strong" else w["cases_per_gpu"]     # one GPU's share
+    pop = ref_arm_pop(w, n_cases)                               # bounded sample: ~2e7 updates per step
     from oracle import binding as ob
     ob.build()
     value, dt = oracle_arm(w, n_cases, pop, args.steps, args.warmup, workers)
-    sample = f"{args.steps} generations at {n_cases} cases with a population subsample of {pop} (cost is linear in pop)"
+    sample = (f"{args.steps} generations at {n_cases} cases with a population subsample of {pop} (cost is linear in pop); "
+              "worker threads persist across calls (main_cpu.go spawns goroutines per call: kinder to the CPU than the reference)")
     line = {
         "impl": "reference", "metric": "individual-case semantic updates/sec", "value": value, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "global_cases": n_cases * max(1, args.gpus), "pop": w["pop"],
-                   "l2": "n/a (CPU arm)", "parallelism": "host threads"},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.workload, w, world, scaling),
         "cpu_baseline": {"value": value, "unit": "updates/s", "cores": workers, "kind": "port", "sample": sample,
                          "note": "C restatement of main_cpu.go (oracle); go-gsgp itself cannot be built (no Go toolchain)"},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -169,6 +191,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak (default): the workload's case count per GPU; strong: that many cases in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-gens", type=int, default=2)
     args = ap.parse_args()
@@ -201,8 +225,13 @@ def main():
 
     w = WORKLOADS[args.workload]
     P, V = w["pop"], w["nvar"]
-    n_local = w["cases_per_gpu"]
-    n_global = n_local * world
+    scaling = args.scaling or ("strong" if w.get("strong") else "weak")
+    if scaling == "strong":                                  # the case count is the job's: every rank holds 1/world of it
+        n_global = w["cases_per_gpu"]
+        n_local = n_global // world                         # (+1 on the first ranks when it does not divide: gsgp_shard_range)
+    else:
+        n_local = w["cases_per_gpu"]
+        n_global = n_local * world
     nrow, nrow_test = int(0.8 * n_global), n_global - int(0.8 * n_global)
     X, y = synth(w["cfg_id"], n_global, V)
 
@@ -327,6 +356,23 @@ def main():
         barrier()
         if rank != 0:
             channel = PlanChannel.attach(ch_name, rank - 1, P, timeout_ms=60000)
+    # first the plain loop a Go host that keeps its own rand.* calls would run: build the plan serially on the host
+    # (gsgph_build_plan = main_cpu.go's per-k dispatch), then gsgp_generation() compiles, uploads, runs, reads back
+    serial = None
+    if not share:
+        Ks = max(3, min(K, 15))
+        for _ in range(3):
+            plan, pool = host.build_plan(fit, best)
+            fit, fit_test, best = e.generation(plan, pool)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ks):
+            plan, pool = host.build_plan(fit, best)
+            fit, fit_test, best = e.generation(plan, pool)
+        barrier()
+        ms_serial = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        serial = {"value": updates_per_step * Ks / (ms_serial * 1e-3), "ms_per_step": ms_serial / Ks, "steps": Ks,
+                  "what": "serial host loop: gsgph_build_plan (the reference's per-k RNG dispatch) then gsgp_generation, no overlap of host and device"}
     planner = None if (share and rank != 0) else (
         host.planner(programs=planner_mode == "programs", n_threads=planner_threads) if planner_mode != "0" else None)
     def replay_step(count=False):
@@ -407,9 +453,15 @@ def main():
         bpu = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
         kname = "gsop_kernel (GS crossover/mutation/reproduction + error reduction)"
     achieved = local_updates * bpu * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this
-    # workload (profiles/README.md); null for workloads that were not captured
-    traffic = {("cfg2", True): 1.744e9, ("cfg2", False): 2.895e9}.get((args.workload, fused)) if world == 1 else None
+    # SURVEY 8(d)'s accounting of the same launches: kernel (c) reads the parents AND R (32 B per computed update) -- the
+    # fused kernel does that work too, with R served from registers instead of HBM
+    bpu_8d = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
+    achieved_8d = local_updates * bpu_8d * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured in this run -- the figure of the committed
+    # `ncu --set full` capture of the same workload and kernel (profiles/README.md), null where there is none
+    traffic_tab = {("cfg2", True): (1.79e9, "profiles/r02_gen_kernel_cfg2_ncu_summary.csv"),
+                   ("cfg2", False): (2.895e9, "profiles/r01_gsop_kernel_final_ncu_summary.csv")}
+    traffic, traffic_src = traffic_tab.get((args.workload, fused), (None, None)) if world == 1 else (None, None)
     n_gu, ms_gu, _ = prof_u[capi.K_GSOP]
     n_iu, ms_iu, _ = prof_u[capi.K_INTERP]
     bpu_u = 32.0 * frac_computed + 16.0 * (1.0 - frac_computed)
@@ -418,17 +470,22 @@ def main():
                   "bound": "hbm", "achieved": ach_u, "peak": peak, "unit": "GB/s", "frac": (ach_u / peak) if ach_u else None,
                   "bytes_per_update": bpu_u, "launches": n_gu, "ms_per_launch": ms_gu / max(1, n_gu),
                   "interp_kernel_ms_per_launch": ms_iu / max(1, n_iu),
-                  "traffic": {("cfg2"): 2.895e9}.get(args.workload) if world == 1 else None,
+                  "traffic": traffic_tab[("cfg2", False)][0] if (world == 1 and args.workload == "cfg2") else None,
+                  "traffic_source": traffic_tab[("cfg2", False)][1] + " (an earlier capture, not this run)" if (world == 1 and args.workload == "cfg2") else None,
                   "note": "same generations with GSGP_PIPELINE=unfused; not the timed `value` path"}
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_update": bpu,
-                "launches": n_gs, "ms_total": ms_gs, "pipeline": "fused" if fused else "unfused",
+                "traffic": traffic, "traffic_source": (traffic_src + " (an earlier capture of this workload, not measured in this run)") if traffic_src else None,
+                "peak_source": peak_src, "bytes_per_update": bpu,
+                "accounting": "bytes the fused kernel has to move: XO 24 B (p1, p2, child), MUT 16 B, copy 16 B per update; R never leaves the SM",
+                "survey_8d": {"bytes_per_update": bpu_8d, "achieved": achieved_8d, "frac": (achieved_8d / peak) if achieved_8d else None,
+                              "accounting": "SURVEY 8(d) kernel (c): 32 B per crossover / mutation update (parents + R read, child written), 16 B per copy"},
+                "launches": n_gs, "ms_total": ms_gs, "ms_per_launch": ms_gs / max(1, n_gs), "pipeline": "fused" if fused else "unfused",
                 "interp_kernel": {"launches": n_it, "ms_total": ms_it},
                 "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None},
-                "limiter": ("issue slots 63 %, shared-memory wavefronts 60-65 %, fp64 pipe 44 %, DRAM 31 % (ncu, profiles/"
-                            "r01_gen_kernel_final_ncu_summary.csv): the fused kernel is balanced across the SM's pipes, not "
-                            "HBM-bound; see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
+                "limiter": ("instruction issue at 6 warps per scheduler (ncu, profiles/r02_gen_kernel_cfg2_ncu_summary.csv): issue slots 64 %, "
+                            "l1tex data pipe 65-70 % (shared-memory operand fetches of the interpreter), fp64 pipe 45 %, DRAM 36 %; "
+                            "see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
                 "gs_kernel_unfused": gs_unfused}
 
     # interpreter work per generation (quoted for config 4): random trees and tree nodes evaluated over every
@@ -446,7 +503,7 @@ def main():
         roofline["interpreter_work"] = {"error": repr(ex)}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:                # rank 0's host cores, at one GPU's share of the cases
         from oracle import binding as ob
         ob.build()
         cores = os.cpu_count() or 1
@@ -466,18 +523,18 @@ def main():
         line = {
             "metric": "individual-case semantic updates/sec", "value": value, "unit": "updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "global_cases": n_global, "pop": P,
-                       "l2": "inputs larger than L2 (semantic store %.2f GB per buffer per GPU)" % (P * n_local * 8 / 1e9),
-                       "store": store, "exchange": exchange,
-                       "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU"},
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.workload, w, world, scaling),
+            "engine": {"store": store, "exchange": exchange, "parallelism": f"case-sharded x{world}" if world > 1 else "single GPU",
+                       "cases_per_gpu": n_local},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / K, "timing": "host wall clock around K generations of the host-replay loop (plan building + gsgp_generation%s with host buffers), loop in %s" % ("_compiled" if planner_mode == "programs" else "", "the compiled host (gsgph_replay_generations)" if compiled_loop else "Python"),
                     "plan_builder": ("pipelined (gsgph_planner_*%s): elite-index guesses right/wrong = %d/%d" %
                                      (", trees compiled ahead: gsgp_generation_compiled" if planner_mode == "programs" else "",
                                       planner_stats["hits"], planner_stats["misses"])) if planner_stats else "serial (gsgph_build_plan)",
                     "plan_sharing": "rank 0 plans, the other ranks read the plan from shared memory (gsgph_channel_*)" if share
-                                    else ("every rank builds the same plan" if world > 1 else "n/a")},
+                                    else ("every rank builds the same plan" if world > 1 else "n/a"),
+                    "serial_host_loop": serial},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "init": {"ms": init_ms[0] if init_ms else None,

@@ -374,6 +374,7 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     a.plan = c->dplan; a.sem_old = sem_old; a.sem_new = sem_new; a.R = c->dR; a.y = c->dy;
     a.partial = c->dpartial; a.pitch = c->pitch; a.r_pitch = c->L.n_pad; a.k0 = k0; a.r_k0 = r_k0; a.n_tiles = c->n_tiles;
     a.mode = mode; a.L = c->L;
+    if (nk > 65535) return fail(c, "gsop_kernel: %d individuals in one launch (the grid's y dimension holds 65535)", nk);
     dim3 grid(c->n_tiles, nk);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
     switch (c->linsc ? GSGP_SUMO : c->cfg.error_measure) {   // linear scaling: this pass only sums the outputs
@@ -550,6 +551,18 @@ int setup_peer_exchange(gsgp_ctx *c)
     if (nccl_gather_bytes(c, &ok, oks.data(), 1)) return 1;
     bool all_ok = want;
     for (unsigned char v : oks) all_ok = all_ok && v;
+    {   // one rank per GPU is a hard requirement of the peer-store exchange: xchg_wait_kernel spins on flags that the
+        // other ranks' reduce kernels raise, and two ranks sharing a GPU could keep each other's kernels off the SMs
+        // (B200_PROFILING.md: cross-launch spin-waits on one GPU end in a context-switch timeout).  Ranks on the same
+        // device (same UUID) therefore take the ncclAllGather path.
+        cudaDeviceProp prop{};
+        CU(c, cudaGetDeviceProperties(&prop, c->cfg.device));
+        std::vector<cudaUUID_t> ids((size_t)W);
+        if (nccl_gather_bytes(c, &prop.uuid, ids.data(), sizeof(cudaUUID_t))) return 1;
+        for (int r = 0; r < W && all_ok; ++r)
+            for (int q = r + 1; q < W; ++q)
+                if (memcmp(&ids[(size_t)r], &ids[(size_t)q], sizeof(cudaUUID_t)) == 0) { all_ok = false; break; }
+    }
     unsigned char opened = all_ok;
     if (all_ok) {
         for (int r = 0; r < W && opened; ++r) {
@@ -1007,6 +1020,11 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         c->post_stride = (1 << (d + 1));                       // nodes <= 2^(d+1)-1
         c->prog_stride = (1 << d);                             // function nodes <= 2^d-1
         c->tree_stride = 4 * (1 << d);                         // ints  <= 4*2^d-3 (main_cpu.go:609-639)
+        // tree offsets inside a draw set's pool are int32 in the plan entries (the ABI's tree0_off / tree1_off)
+        if ((int64_t)2 * P * c->tree_stride > INT32_MAX || (int64_t)2 * P * c->prog_stride > INT32_MAX) {
+            fail(c, "device RNG mode: population %d x depth %d needs tree pools beyond 2^31 entries", P, d);
+            return bail();
+        }
         for (int i = 0; i < kDrawSets; ++i) {
             CUC(cudaMalloc((void **)&c->ds[i].tree_pool, sizeof(int32_t) * 2 * (size_t)P * c->tree_stride));
             CUC(c->ds[i].prog_pool.reserve((size_t)2 * P * c->prog_stride));

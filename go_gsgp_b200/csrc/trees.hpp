@@ -88,8 +88,12 @@ inline bool compile_prefix_tree(const int32_t *tree, int32_t len, int32_t n_symb
         return true;
     }
     if (need.size() < (size_t)len) need.resize((size_t)len);
-    // pass 1: post-order over the function nodes
-    int32_t visited = 0;
+    // pass 1: post-order over the function nodes.  A tree of f function nodes fills 4 f + 1 array words (3 per function
+    // node, f + 1 terminals), and the callers reserve len / 4 + 1 instructions per tree: an array whose child indices
+    // share nodes (a DAG: forward pointers, no cycle) would expand into more function-node visits than that, so the
+    // walk stops at (len - 1) / 4 of them -- no array can make the emission below write past what was reserved.
+    int32_t visited = 0, n_func = 0;
+    const int32_t max_func = (len - 1) / 4;
     frames.clear();
     frames.push_back(TreeFrame{0, 0, 0, 0, 0});
     while (!frames.empty()) {
@@ -98,6 +102,7 @@ inline bool compile_prefix_tree(const int32_t *tree, int32_t len, int32_t n_symb
         if (f.state == 0) {
             if (p + 2 >= len) { err = "truncated function node"; return false; }
             if (++visited > len) { err = "tree has a cycle"; return false; }
+            if (++n_func > max_func) { err = "tree nodes are shared or overlap (more function nodes than the array holds)"; return false; }
         }
         if (f.state < 2) {                                // visit child f.state (0 = left, 1 = right)
             const int32_t c = tree[p + 1 + f.state];

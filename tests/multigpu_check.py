@@ -28,12 +28,14 @@ def main():
         dist.broadcast(buf, 0)
         return bytes(buf.cpu().numpy().tobytes())
 
-    for rng_kind, mode in ((ob.RNG_ALFG, capi.RNG_HOST_REPLAY), (ob.RNG_PHILOX, capi.RNG_DEVICE_PHILOX)):
-        X, y, nrow = synth_dataset(2, 20_003, 7, nrow=15_001)          # ragged: shards of unequal size
+    # two shapes, both ragged (shards of unequal size; 8 ranks get 7 tiles each of the first, ~100 of the second)
+    shapes = ((20_003, 15_001, 7, 64, 6), (200_011, 160_003, 20, 24, 3))
+    for (n_cases, n_train, n_var, P, gens), (rng_kind, mode) in (
+            (sh, rm) for sh in shapes for rm in ((ob.RNG_ALFG, capi.RNG_HOST_REPLAY), (ob.RNG_PHILOX, capi.RNG_DEVICE_PHILOX))):
+        X, y, nrow = synth_dataset(2, n_cases, n_var, nrow=n_train)
         N, V = X.shape
-        P = 64
         cfg = ob.make_config(population_size=P, rng_kind=rng_kind, rng_seed=5, error_measure=ob.RMSE,
-                             use_linear_scaling=int(mode == capi.RNG_DEVICE_PHILOX))
+                             use_linear_scaling=int(mode == capi.RNG_DEVICE_PHILOX), n_workers=max(1, (os.cpu_count() or 1) // world))
         o = ob.Oracle(cfg, X, y, nrow)
         o.create_T_F()
         e = Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=capi.RMSE, rng_seed=5,
@@ -53,7 +55,7 @@ def main():
         assert same_best(best, o) and np.all(rel_err(fit, o.fit()) <= 1e-9)
         tr_lo, tr_hi = Engine.shard_range(nrow, rank, world)
         te_lo, te_hi = Engine.shard_range(N - nrow, rank, world)
-        for g in range(6):
+        for g in range(gens):
             o.generation()
             if mode == capi.RNG_HOST_REPLAY:
                 fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())

@@ -436,20 +436,19 @@ def test_error_behaviour():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-def test_multi_gpu_case_sharding_matches_oracle(exchange):
-    """N>1: case-sharded engines against the global oracle; the partial sums travel as direct stores into the peers'
-    buffers from the reduction kernel (default) or through ncclAllGather (GSGP_EXCHANGE=nccl)."""
+def test_multi_gpu_case_sharding_matches_oracle(exchange, world):
+    """N>1: case-sharded engines against the global oracle at 2, 4 and 8 ranks; the partial sums travel as direct stores
+    into the peers' buffers from the reduction kernel (default) or through ncclAllGather (GSGP_EXCHANGE=nccl)."""
     import subprocess
     import sys
     import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs on the box")
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs on the box")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(os.path.dirname(__file__), "multigpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, GSGP_EXCHANGE=exchange))
+           "--master-addr", "127.0.0.1", "--master-port", str(29517 + world), os.path.join(os.path.dirname(__file__), "multigpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, GSGP_EXCHANGE=exchange))
     assert out.returncode == 0 and f"MULTIGPU_OK world={world} exchange={exchange}" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
@@ -978,3 +977,98 @@ def test_compiled_replay_loop_equals_stepping_from_python():
         outs.append((hist, fit.tobytes(), fit_test.tobytes(), best, e.generation_index))
         e.close(); h.close()
     assert outs[0] == outs[1]
+
+
+# ---- lock step with the oracle at the benchmarked shapes (BASELINE.json configs 2-5) -------------------------------
+# Oracle-made random plans (its own draws of operators, tournaments, random trees) replayed on the CUDA path, and the
+# device-RNG mode against the oracle's Philox streams, at the case counts bench.py times: the kernels' size-dependent
+# paths (interior / ragged tiles, the train | test boundary inside a tile, hundreds of work items per launch, blocks of
+# tiles of the single-buffer store, int64 row pitches) see the same comparison as the small shapes above.  Populations
+# are small because the oracle costs ~1 s per million updates; the kernels' work decomposition is per (individual,
+# tile) and does not depend on the population beyond the number of items.
+def _oracle_workers():
+    return min(16, os.cpu_count() or 1)
+
+
+def test_cfg2_shape_lockstep_100k_cases():
+    """config 2: 20 vars x 100k cases (80k train / 20k test), depth 6, p_xo 0.6 / p_mut 0.3; pop 48, 5 generations,
+    host replay and device mode."""
+    X, y, nrow = synth_dataset(2, 100_000, 20)
+    o, e, _ = _mk(X, y, nrow, population_size=48, seed=2, n_workers=_oracle_workers())
+    _lockstep_replay(o, e, 5)
+    assert_close(e.get_semantics(), o.semantics(), TOL, "cfg2 replay semantics")
+    e.close(); o.close()
+    o, e, _ = _mk(X, y, nrow, population_size=48, seed=2, rng_kind=ob.RNG_PHILOX, n_workers=_oracle_workers())
+    for g in range(5):
+        o.generation()
+        e.run_generations(1)
+        want, got = o.last_plan(), e.get_plan()
+        for f in ("op", "elite", "tree0_len", "tree1_len"):
+            np.testing.assert_array_equal(got[f], want[f], err_msg=f"gen {g} plan.{f}")
+        live = want["elite"] == 0
+        for f in ("p1", "p2"):
+            np.testing.assert_array_equal(got[f][live], want[f][live], err_msg=f"gen {g} plan.{f}")
+        fit, fit_test, best = e.get_fitness()
+        assert_close(fit, o.fit(), TOL, f"gen {g} fit"); assert_close(fit_test, o.fit_test(), TOL, f"gen {g} fit_test")
+        assert same_best(best, o)
+    assert_close(e.get_semantics(), o.semantics(), TOL, "cfg2 device-mode semantics")
+    e.close(); o.close()
+
+
+@pytest.mark.parametrize("kw", [
+    # config 4: depth-8 trees over the full function set (protected division included), two trees per individual
+    dict(max_depth_creation=8, p_crossover=0.0, p_mutation=1.0, init_type=1),
+    # config 3: semantic feeding -- half of the population seeded with precomputed semantics, depth 6
+    dict(max_depth_creation=6, n_seeds=8),
+])
+def test_million_case_shapes_lockstep(kw):
+    """configs 3 / 4: 1M cases (ragged: 1 000 003, so the last tile and the train | test boundary are partial),
+    pop 16, 3 generations of oracle-made plans; then the same run in device mode."""
+    kw = dict(kw)
+    n_seeds = kw.pop("n_seeds", 0)
+    N = 1_000_003
+    X, y, nrow = synth_dataset(3, N, 20, nrow=800_001)
+    rng = np.random.default_rng(7)
+    seeds = [y + rng.normal(0.0, 0.05 + 0.001 * k, size=N) for k in range(n_seeds)]
+    for rng_kind in (ob.RNG_ALFG, ob.RNG_PHILOX):
+        o, e, (fit, fit_test, best) = _mk(X, y, nrow, population_size=16, seed=4, rng_kind=rng_kind, seeds=seeds,
+                                          n_workers=_oracle_workers(), **kw)
+        assert_close(fit, o.fit(), TOL, "initial fit"); assert same_best(best, o)
+        for g in range(3):
+            o.generation()
+            if rng_kind == ob.RNG_ALFG:
+                fit, fit_test, best = e.generation(o.last_plan(), o.last_tree_pool())
+            else:
+                e.run_generations(1)
+                fit, fit_test, best = e.get_fitness()
+            assert_close(fit, o.fit(), TOL, f"gen {g} fit"); assert_close(fit_test, o.fit_test(), TOL, f"gen {g} fit_test")
+            assert same_best(best, o)
+        for i in (0, 5, 15):
+            assert_close(e.get_semantic(i), o.semantic(i), TOL, f"sem[{i}]")
+        e.close(); o.close()
+
+
+def test_single_buffer_store_at_a_million_cases():
+    """config 5's store (one buffer + a block of free cases) at 1M cases with the generation cut into five
+    blocks of case tiles: lock step with the oracle over 4 generations (rows shift right, left, right, left), and
+    bit-identical to the two-buffer store."""
+    g = _engine_mod()
+    N = 1_000_003
+    X, y, nrow = synth_dataset(5, N, 20, nrow=800_001)
+    n_tiles = (800_016 + 200_016 + 255) // 256
+    os.environ["GSGP_SHIFT_TILES"] = str(n_tiles // 5 + 1)            # five launches per generation
+    try:
+        o, e, _ = _mk(X, y, nrow, population_size=12, seed=6, flags=g.capi.FLAG_SINGLE_BUFFER_STORE, n_workers=_oracle_workers())
+        assert e.store_buffers == 1
+        _lockstep_replay(o, e, 4, check_sem_every=2)
+        single = e.get_semantics()
+        assert_close(single, o.semantics(), TOL, "single-buffer semantics at 1M cases")
+        plans = [(o.last_plan().copy(), o.last_tree_pool().copy())]
+        e.close()
+    finally:
+        os.environ.pop("GSGP_SHIFT_TILES", None)
+    # the same run on two buffers: bit-identical rows
+    o2, e2, _ = _mk(X, y, nrow, population_size=12, seed=6, n_workers=_oracle_workers())
+    _lockstep_replay(o2, e2, 4, check_sem_every=4)
+    np.testing.assert_array_equal(e2.get_semantics(), single)
+    e2.close(); o2.close(); o.close()

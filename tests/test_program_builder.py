@@ -103,7 +103,9 @@ def test_programs_reproduce_oracle_tree_semantics(depth, nconst, zero_depth):
 
 
 def test_malformed_trees_are_rejected():
-    for bad in ([0, 3, 4, 4], [0, 1, 2], [0, 3, 4, 99, 4], [0, 0, 0, 4, 4], [9]):
+    # the last three share nodes between parents (a DAG): they would expand into more instructions than len / 4 + 1
+    for bad in ([0, 3, 4, 4], [0, 1, 2], [0, 3, 4, 99, 4], [0, 0, 0, 4, 4], [9], [0, 3, 3, 1, 6, 6, 4], [0, 3, 3, 4],
+                [0, 3, 3, 1, 6, 6, 2, 9, 9, 4]):
         with pytest.raises(ValueError):
             compile_tree(bad, 6)
 
