@@ -207,7 +207,6 @@ struct gsgp_ctx {
     // (alternately right and left), one block of `shift` cases per launch in the order that only ever overwrites
     // cases whose old values every individual has already consumed.  Memory = (1 + shift/n_pad) x the store, no copies.
     bool single_store = false;
-    bool gen_tmem = false;                                        // gen_kernel keeps the X tile in tensor memory (tcgen05.ld operand fetches)
     int32_t gen_warps = 16;                         // warps per gen_kernel block
     int32_t shift_tiles = 0;                                  // case tiles (256 cases) per block
     int64_t pitch = 0;                                        // row pitch of the store in doubles
@@ -387,27 +386,24 @@ int launch_gsop(gsgp_ctx *c, int mode, int32_t k0, int32_t nk, int32_t r_k0, con
     return 0;
 }
 
-// fused pipeline: shared memory of one gen_kernel block for `ipg` individuals per group (tmem: the X tile lives in tensor memory)
-size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps, bool tmem)
+// fused pipeline: shared memory of one gen_kernel block for `ipg` individuals per group
+size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t warps)
 {
     const size_t ncol = (size_t)c->cfg.nvar + c->cfg.num_constants;
     const size_t per_warp = ((size_t)levels * kPass + 2 * 2 * kGenProgSlots) * sizeof(double);
-    return (tmem ? 0 : (ncol + 1) * kPass * sizeof(double)) + per_warp * warps + (size_t)ipg * (sizeof(GenSlot) + 8) + sizeof(uint64_t) + 16 + 4 * kCostBuckets;
+    return (ncol + 1) * kPass * sizeof(double) + per_warp * warps + (size_t)ipg * (sizeof(GenSlot) + 8) + sizeof(uint64_t) + 16 +
+           4 * kCostBuckets;
 }
 
 // the instantiated block sizes of gen_kernel (warps per block, one block per SM)
-#define GSGP_GEN_WARPS(X) X(16) X(20) X(24) X(28)
+#define GSGP_GEN_WARPS(X) X(24) X(20) X(16) X(12)
 
 template <int MEASURE>
 int launch_gen_kernel(gsgp_ctx *c, dim3 grid, size_t smem, const GenArgs &a)
 {
-#define GSGP_LAUNCH(W) if (c->gen_warps == W) { \
-        if (c->gen_tmem) gen_kernel<MEASURE, W, true><<<grid, W * 32, smem, c->stream>>>(a); \
-        else gen_kernel<MEASURE, W, false><<<grid, W * 32, smem, c->stream>>>(a); \
-        return 0; }
+#define GSGP_LAUNCH(W) if (c->gen_warps == W) { gen_kernel<MEASURE, W><<<grid, W * 32, smem, c->stream>>>(a); return 0; }
     GSGP_GEN_WARPS(GSGP_LAUNCH)
 #undef GSGP_LAUNCH
-    if (c->gen_warps == 12 && !c->gen_tmem) { gen_kernel<MEASURE, 12, false><<<grid, 12 * 32, smem, c->stream>>>(a); return 0; }
     return fail(c, "gen_kernel: %d warps per block is not instantiated", c->gen_warps);
 }
 
@@ -415,11 +411,9 @@ template <int MEASURE>
 cudaError_t gen_kernels_allow_smem(int bytes)
 {
     cudaError_t e = cudaSuccess;
-#define GSGP_ATTR(W) if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-                     if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#define GSGP_ATTR(W) if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     GSGP_GEN_WARPS(GSGP_ATTR)
 #undef GSGP_ATTR
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gen_kernel<MEASURE, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 
@@ -433,8 +427,7 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
     int32_t groups = std::max(1, (target + n_blocks - 1) / n_blocks);
     groups = std::min(groups, std::max(1, (nk + c->gen_warps - 1) / c->gen_warps));   // >= one individual per warp
     int32_t ipg = (nk + groups - 1) / groups;
-    const size_t smem_cap = c->gen_warps <= 12 ? (size_t)112 * 1024 : (size_t)227 * 1024;    // 12 warps: two blocks per SM
-    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_tmem) > smem_cap) ipg = (ipg + 1) / 2;
+    while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
     groups = (nk + ipg - 1) / ipg;
     if (groups > 65535) return fail(c, "population chunk too large for one launch");
     GenArgs a{};
@@ -443,7 +436,7 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
     a.sem_old = sem_old; a.sem_new = sem_new; a.pitch = c->pitch; a.tile_begin = tile_begin;
     a.partial = c->dpartial;
     a.k0 = k0; a.nk = nk; a.inds_per_group = ipg; a.n_tiles = c->n_tiles_gen; a.smem_levels = c->gen_levels; a.L = c->L;
-    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps, c->gen_tmem);
+    const size_t smem = gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps);
     dim3 grid(n_blocks, groups);
     ProfScope ps(c, GSGP_K_GSOP, bytes);
     int rc;
@@ -946,16 +939,15 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         // warps per gen_kernel block (one block per SM): the kernel is bound by its warps' issue rate, so as many as the
         // register file carries without spills; fewer when the dataset's columns leave less shared memory.
         // GSGP_GEN_WARPS picks one of the instantiated sizes (A/B runs).
-        // The X tile lives in tensor memory when its columns (+ constants + the targets) fit the SM's 512 TMEM columns,
-        // 16 each; wider datasets stage it in shared memory.  GSGP_GEN_OPERANDS=smem forces the latter (A/B runs).
+        // warps per gen_kernel block (one block per SM): the kernel is bound by its warps' issue rate, so as many as the
+        // register file carries (24 x 80 registers); fewer when the dataset's columns leave less shared memory.
+        // GSGP_GEN_WARPS picks one of the instantiated sizes (A/B runs).
         bool fits = false;
         const int env_w = getenv("GSGP_GEN_WARPS") ? atoi(getenv("GSGP_GEN_WARPS")) : 0;
-        const char *opnd = getenv("GSGP_GEN_OPERANDS");
-        c->gen_tmem = cfg->nvar + cfg->num_constants + 1 <= kTmemMaxOperands && !(opnd && strcmp(opnd, "smem") == 0);
-        for (int w : {env_w, 24, 20, 16}) {
+        for (int w : {env_w, 24, 20, 16, 12}) {
             if (w <= 0) continue;
             c->gen_warps = w;
-            fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps, c->gen_tmem) <= (size_t)kMaxSmem;
+            fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps) <= (size_t)kMaxSmem;
             if (fits || w == env_w) break;
         }
         c->fused = !(cfg->flags & GSGP_FLAG_KEEP_TREE_SEMANTICS) && !(pl && strcmp(pl, "unfused") == 0) && fits;

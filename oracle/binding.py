@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
         "orc_set_initial_tree": (None, [vp, C.c_int32, ip, C.c_int32]),
         "orc_generation": (None, [vp]),
         "orc_generation_replay": (None, [vp, C.c_void_p, ip]),
+        "orc_effects_step": (None, [vp, C.c_int]),
         "orc_set_exp_kind": (None, [C.c_int]),
         "orc_exp64": (C.c_double, [C.c_double]),
         "orc_sigmoid": (C.c_double, [C.c_double]),
@@ -233,6 +234,10 @@ class Oracle:
     # --- generation loop ---------------------------------------------------------------
     def generation(self):
         self.L.orc_generation(self.h)
+
+    def effects_step(self, test_crossover: bool):
+        """operators_effects.go's single step (:783-806,836-842,1246-1256); last_plan() / last_tree_pool() hold its draws"""
+        self.L.orc_effects_step(self.h, int(bool(test_crossover)))
 
     def generation_replay(self, plan: np.ndarray, pool: np.ndarray):
         plan = np.ascontiguousarray(plan)

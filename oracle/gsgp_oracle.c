@@ -842,6 +842,48 @@ void orc_generation(orc_state *s)
     s->generation++;
 }
 
+/* operators_effects.go's single step (its main, :1246-1256): every individual gets the same operator once, parents
+ * drawn UNIFORMLY (random_selection :783-786), no tournament and no operator draw.  test_crossover != 0:
+ * geometric_semantic_crossover(k) for every k (:800-806: tree, p1 = Intn(P), p2 = Intn(P), in that order); else
+ * reproduction(k) -- a plain self copy there (:790-797: no draw) -- then geometric_semantic_mutation(k) (:836-842:
+ * ms = Float64(), rt1, rt2).  index_best is never assigned in that program (its zero value, individual 0, plays the
+ * elite: :801,:837).  Records the plan and tree pool like orc_generation; fit / fit_test then hold fit_new / fit_test_new
+ * of the step (the program prints fit[k] fit_new[k], :1258-1261). */
+void orc_effects_step(orc_state *s, int test_crossover)
+{
+    int32_t P = s->cfg.population_size;
+    s->pool_len = 0;
+    s->index_best = 0;
+    for (int32_t k = 0; k < P; ++k) {
+        orc_plan_entry *e = &s->plan[k];
+        memset(e, 0, sizeof *e);
+        e->p1 = k; e->p2 = -1; e->tree0_off = e->tree1_off = -1;
+        e->elite = (k == s->index_best);
+        if (test_crossover) {
+            e->op = ORC_OP_XO;
+            if (k != s->index_best) {
+                e->tree0_off = pool_new_tree(s, &e->tree0_len);           /* :803 */
+                e->p1 = orc_rng_intn(&s->rng, P);                         /* :805 random_selection */
+                e->p2 = orc_rng_intn(&s->rng, P);                         /* :806 */
+                xo_apply(s, k, e->p1, e->p2, s->pool + e->tree0_off);
+            } else {
+                copy_individual(s, k, k);
+            }
+        } else {
+            e->op = ORC_OP_MUT;
+            copy_individual(s, k, k);                                     /* reproduction(i): self copy, :790-797 */
+            if (k != s->index_best) {
+                e->ms = orc_rng_float64(&s->rng);                         /* :838 */
+                e->tree0_off = pool_new_tree(s, &e->tree0_len);           /* :840 */
+                e->tree1_off = pool_new_tree(s, &e->tree1_len);           /* :841 */
+                mut_apply(s, k, e->ms, s->pool + e->tree0_off, s->pool + e->tree1_off);
+            }
+        }
+    }
+    update_tables(s);
+    s->generation++;
+}
+
 void orc_generation_replay(orc_state *s, const orc_plan_entry *plan, const int32_t *tree_pool)
 {
     int32_t P = s->cfg.population_size;

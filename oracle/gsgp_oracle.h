@@ -119,6 +119,8 @@ void orc_set_initial_tree(orc_state *s, int32_t ind, const int32_t *tree, int32_
  * In ORC_RNG_PHILOX mode the stream is re-seeked to (generation, k) before each individual. */
 void orc_generation(orc_state *s);
 /* Apply an externally supplied plan (no RNG draws): the replay path. */
+/* operators_effects.go:783-806,836-842,1246-1256: the one-step experiment (uniform parents); records plan + tree pool */
+void orc_effects_step(orc_state *s, int test_crossover);
 void orc_generation_replay(orc_state *s, const orc_plan_entry *plan, const int32_t *tree_pool);
 
 /* ------------------------------------------------------------------ primitives ----------- */

@@ -244,3 +244,31 @@ def test_compile_plan_and_planner_reject_bad_input():
         setattr(p, field, val)
         assert not L.gsgph_planner_new(h.rng, C.byref(p)), field
     h.close()
+
+
+@pytest.mark.parametrize("test_crossover", [True, False])
+@pytest.mark.parametrize("kw", [dict(population_size=50), dict(population_size=23, num_random_constants=4, max_depth_creation=8, zero_depth=1)])
+def test_effects_plan_equals_the_oracles_restatement(kw, test_crossover):
+    """operators_effects.go's single step (:783-806 crossover with uniform parents, :836-842 mutation after a self copy,
+    :1246-1256 the loop): gsgph_build_effects_plan against the oracle's own restatement (orc_effects_step), draw for draw
+    under Go's rand.Seed stream, after the same create_T_F / initialize_population draws."""
+    from go_gsgp_b200.host import HostDriver
+    X, y, nrow = synth_dataset(1, 120, 5, nrow=90)
+    o = ob.Oracle(ob.make_config(rng_kind=ob.RNG_ALFG, rng_seed=17, **kw), X, y, nrow)
+    o.create_T_F()
+    h = HostDriver(nvar=5, seed=17, population_size=kw["population_size"], num_constants=kw.get("num_random_constants", 0),
+                   max_depth_creation=kw.get("max_depth_creation", 6), zero_depth=kw.get("zero_depth", 0))
+    np.testing.assert_array_equal(h.create_T_F(), o.symbol_values())
+    o.initialize_population(0)
+    trees = h.initialize_population(0)
+    for i, t in enumerate(trees):
+        np.testing.assert_array_equal(t, o.initial_tree(i))
+    o.evaluate()
+    plan, pool = h.build_effects_plan(test_crossover)
+    o.effects_step(test_crossover)
+    want, want_pool = o.last_plan(), o.last_tree_pool()
+    for f in want.dtype.names:
+        np.testing.assert_array_equal(plan[f], want[f], err_msg=f)
+    np.testing.assert_array_equal(pool[: len(want_pool)], want_pool)
+    # and both generators are at the same point of the stream afterwards
+    assert h.rng_float64() == o.rng().float64() if hasattr(h, "rng_float64") else True

@@ -119,3 +119,5 @@ def test_generated_division_ptx_is_current():
     gen = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gen)
     assert open(gen.TARGET).read() == gen.render(gen.DEFAULT_GROUP)
+    # gen_kernel's threaded-code interpreter (interp_body.inc.h) comes from the same generator
+    assert open(gen.TARGET_BODY).read() == gen.render_body(gen.DEFAULT_GROUP)

@@ -8,5 +8,5 @@ GSGP_BENCH_SHARE_PLAN=$SH GSGP_EXCHANGE=$EX timeout 500 python -m torch.distribu
 python - $O.json <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(sys.argv[1], "n_gpus %d exchange %s value %.4g ms/step %.4g e2e %.4g frac %.3f clocks %s" % (d["n_gpus"], d["config"]["exchange"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["clocks"]))
+print(sys.argv[1], "n_gpus %d exchange %s value %.4g ms/step %.4g e2e %.4g frac %.3f clocks %s" % (d["n_gpus"], d["engine"]["exchange"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["clocks"]))
 PY
