@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="weak (default): the workload's case count per GPU; strong: that many cases in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-unfused", action="store_true", help="skip the unfused-pipeline leg (roofline.gs_kernel_unfused stays empty)")
     ap.add_argument("--cpu-baseline-gens", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -332,7 +333,7 @@ def main():
     # kernel on its own, for the roofline target north_star states for it --------------------------------
     Ku = max(3, min(K, 10))
     prof_u = {capi.K_INTERP: (0, 0.0, 0.0), capi.K_GSOP: (0, 0.0, 0.0)}
-    if store["buffers"] == 2:                                # the unfused pipeline needs the cur/new pair
+    if store["buffers"] == 2 and not args.no_unfused:        # the unfused pipeline needs the cur/new pair
         e, _, _ = setup(capi.RNG_DEVICE_PHILOX, "unfused")
         e.run_generations(W)
         e.sync()

@@ -9,7 +9,7 @@ run() {   # run <n_gpus> <workload> <steps> <tag> [env...]
     env "$@" timeout 400 python bench.py --workload $W --steps $S --warmup 3 --no-cpu-baseline > $O.json 2> $O.err || { echo "FAILED $O"; tail -5 $O.err; }
   else
     env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) \
-      bench.py --gpus $N --workload $W --steps $S --warmup 3 --no-cpu-baseline > $O.json 2> $O.err || { echo "FAILED $O"; tail -5 $O.err; }
+      bench.py --gpus $N --workload $W --steps $S --warmup 3 --no-cpu-baseline --no-unfused > $O.json 2> $O.err || { echo "FAILED $O"; tail -5 $O.err; }
   fi
   python tools/show_bench.py $O.json
 }
