@@ -213,6 +213,8 @@ struct gsgp_ctx {
     double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
     double *dR = nullptr;
     double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
+    unsigned char *dpack = nullptr; size_t pack_bytes = 0;        // one allocation: dplan | dprog_off | ds[0].prog_desc
+    PinnedBuf<unsigned char> hpack;                               // its pinned image (gsgp_generation_compiled)
     gsgp_plan_entry *dplan = nullptr;
     // random trees + programs of a generation.  Host replay uses set 0; device mode rotates through three sets:
     // generation g is consumed from set g%3 while plan_draw_kernel fills the sets of g+1 and g+2 on the second
@@ -679,7 +681,8 @@ int launch_best(gsgp_ctx *c, int buf, int32_t gen, bool best_done = false)
     if (!best_done) {
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
         best_kernel<<<1, 1024, 0, c->stream>>>(c->dfit[buf], c->dfit_test[buf], c->cfg.population_size,
-                                               c->cfg.minimization_problem, c->dindex_best, c->dhist + gen);
+                                               c->cfg.minimization_problem, c->dindex_best, c->dhist + gen,
+                                               reinterpret_cast<int32_t *>(c->dfit[buf] + 2 * (size_t)c->cfg.population_size));
         CU(c, cudaGetLastError());
     }
     if (c->keep_run) {                                        // best-of-generation semantic + this generation's decisions
@@ -986,9 +989,9 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
             CUC(cudaMalloc((void **)&c->dsem[b], sizeof(double) * (size_t)c->pitch * P));
             CUC(cudaMemsetAsync(c->dsem[b], 0, sizeof(double) * (size_t)c->pitch * P, c->stream));
         }
-        CUC(cudaMalloc((void **)&c->dfit[b], sizeof(double) * 2 * P));           // fit | fit_test: one readback
+        CUC(cudaMalloc((void **)&c->dfit[b], sizeof(double) * (2 * (size_t)P + 1)));   // fit | fit_test | best index: one readback
         c->dfit_test[b] = c->dfit[b] + P;
-        CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * 2 * P, c->stream));
+        CUC(cudaMemsetAsync(c->dfit[b], 0, sizeof(double) * (2 * (size_t)P + 1), c->stream));
     }
     CUC(cudaMalloc((void **)&c->dpartial, sizeof(double) * 2 * (size_t)P * std::max(c->n_tiles, c->n_tiles_gen)));
     CUC(cudaMalloc((void **)&c->dsums, sizeof(double) * 2 * P));
@@ -996,11 +999,16 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMalloc((void **)&c->dsums2, sizeof(double) * 2 * P));
     CUC(cudaMalloc((void **)&c->dsums_all2, sizeof(double) * 2 * P * (size_t)cfg->world_size));
     CUC(cudaMalloc((void **)&c->dab, sizeof(double) * 2 * P));
-    CUC(cudaMalloc((void **)&c->dplan, sizeof(gsgp_plan_entry) * P));
-    CUC(cudaMemsetAsync(c->dplan, 0, sizeof(gsgp_plan_entry) * P, c->stream));
-    CUC(cudaMalloc((void **)&c->dprog_off, sizeof(int32_t) * 2 * P));
+    // plan | program offsets | program descriptors of draw set 0 sit in ONE allocation: a host-replay generation uploads
+    // the three with a single copy (gsgp_generation_compiled)
+    c->pack_bytes = sizeof(gsgp_plan_entry) * (size_t)P + 2 * sizeof(int32_t) * 2 * (size_t)P;
+    CUC(cudaMalloc((void **)&c->dpack, c->pack_bytes));
+    CUC(cudaMemsetAsync(c->dpack, 0, c->pack_bytes, c->stream));
+    c->dplan = reinterpret_cast<gsgp_plan_entry *>(c->dpack);
+    c->dprog_off = reinterpret_cast<int32_t *>(c->dpack + sizeof(gsgp_plan_entry) * (size_t)P);
+    c->ds[0].prog_desc = c->dprog_off + 2 * (size_t)P;
     const int n_sets = cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX ? kDrawSets : 1;
-    for (int i = 0; i < n_sets; ++i) {
+    for (int i = 1; i < n_sets; ++i) {
         CUC(cudaMalloc((void **)&c->ds[i].prog_desc, sizeof(int32_t) * 2 * P));
         CUC(cudaMemsetAsync(c->ds[i].prog_desc, 0, sizeof(int32_t) * 2 * P, c->stream));
     }
@@ -1094,12 +1102,12 @@ void gsgp_destroy(gsgp_ctx *c)
     cudaFree(c->dsums2); cudaFree(c->dsums_all2); cudaFree(c->dab);
     for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) cudaStreamSynchronize(c->draw_stream[i]);
     for (int i = 0; i < kDrawSets; ++i) {
-        cudaFree(c->ds[i].tree_pool); cudaFree(c->ds[i].prog_desc); cudaFree(c->ds[i].rec); cudaFree(c->ds[i].cand);
+        cudaFree(c->ds[i].tree_pool); if (i > 0) cudaFree(c->ds[i].prog_desc); cudaFree(c->ds[i].rec); cudaFree(c->ds[i].cand);   // set 0's descriptors live in dpack
         if (c->ev_draw[i]) cudaEventDestroy(c->ev_draw[i]);
     }
     for (int i = 0; i < kDrawSets; ++i) if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) cudaStreamDestroy(c->draw_stream[i]);
-    cudaFree(c->dplan); cudaFree(c->dprog_off);
+    cudaFree(c->dpack);                                               // dplan | dprog_off | ds[0].prog_desc
     cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
     for (double *p : c->run_sem) cudaFree(p);
     for (gsgp_plan_entry *p : c->run_plan) cudaFree(p);
@@ -1299,18 +1307,22 @@ int gsgp_eval_trees(gsgp_ctx *c, int32_t n, const int32_t *tree_pool, int32_t po
 static int read_fitness(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_best)
 {
     const int P = c->cfg.population_size;
-    CU(c, c->hfit.reserve(2 * (size_t)P)); CU(c, c->hint.reserve(4));
-    if (fit && fit_test) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * 2 * P, cudaMemcpyDeviceToHost, c->stream));
-    else if (fit) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
-    else if (fit_test) CU(c, cudaMemcpyAsync(c->hfit.p + P, c->dfit_test[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
-    if (index_best) CU(c, cudaMemcpyAsync(c->hint.p, c->dindex_best, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, c->hfit.reserve(2 * (size_t)P + 1)); CU(c, c->hint.reserve(4));
+    // fit | fit_test | best index (the kernels that find the best individual leave its index behind the two vectors): the
+    // usual request is one copy
+    if (fit && fit_test) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * (2 * (size_t)P + (index_best ? 1 : 0)), cudaMemcpyDeviceToHost, c->stream));
+    else {
+        if (fit) CU(c, cudaMemcpyAsync(c->hfit.p, c->dfit[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+        if (fit_test) CU(c, cudaMemcpyAsync(c->hfit.p + P, c->dfit_test[c->cur], sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+        if (index_best) CU(c, cudaMemcpyAsync(c->hfit.p + 2 * (size_t)P, c->dfit[c->cur] + 2 * (size_t)P, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
     c->hint.p[1] = 0;
     if (c->p2p) CU(c, cudaMemcpyAsync(c->hint.p + 1, c->xerr, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->hint.p[1]) return fail(c, "peer exchange timed out: a rank did not deliver its partial sums");
     if (fit) memcpy(fit, c->hfit.p, sizeof(double) * P);
     if (fit_test) memcpy(fit_test, c->hfit.p + P, sizeof(double) * P);
-    if (index_best) *index_best = c->hint.p[0];
+    if (index_best) memcpy(index_best, c->hfit.p + 2 * (size_t)P, sizeof(int32_t));
     return 0;
 }
 
@@ -1332,7 +1344,7 @@ int gsgp_fitness_all(gsgp_ctx *c, double *fit, double *fit_test, int32_t *index_
 // gsgp_generation / gsgp_generation_compiled: `programs` == NULL -> the trees are compiled here (staging workers)
 static int generation_impl(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
                            const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off, const int32_t *prog_desc_in,
-                           double *fit_out, double *fit_test_out, int32_t *index_best_out)
+                           double *fit_out, double *fit_test_out, int32_t *index_best_out, bool trusted_programs = false)
 {
     if (check_ready(c)) return 1;
     static const bool trace = getenv("GSGP_TRACE") != nullptr;
@@ -1341,7 +1353,17 @@ static int generation_impl(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32
     if (!c->fitness_valid) return fail(c, "population not evaluated (gsgp_fitness_all)");
     if (!plan) return fail(c, "null plan");
     const int P = c->cfg.population_size;
-    CU(c, c->hplan.reserve(P)); CU(c, c->hoff.reserve(2 * (size_t)P)); CU(c, c->hlen.reserve(2 * (size_t)P));
+    // staging: the compiled path fills one pinned image of the device's plan | offsets | descriptors block
+    gsgp_plan_entry *hplan; int32_t *hoff, *hlen;
+    if (programs) {
+        CU(c, c->hpack.reserve(c->pack_bytes));
+        hplan = reinterpret_cast<gsgp_plan_entry *>(c->hpack.p);
+        hoff = reinterpret_cast<int32_t *>(c->hpack.p + sizeof(gsgp_plan_entry) * (size_t)P);
+        hlen = hoff + 2 * (size_t)P;
+    } else {
+        CU(c, c->hplan.reserve(P)); CU(c, c->hoff.reserve(2 * (size_t)P)); CU(c, c->hlen.reserve(2 * (size_t)P));
+        hplan = c->hplan.p; hoff = c->hoff.p; hlen = c->hlen.p;
+    }
     std::vector<int32_t> &off = c->st_off, &len = c->st_len;
     off.resize(2 * (size_t)P); len.resize(2 * (size_t)P);
     for (int k = 0; k < P; ++k) {
@@ -1355,7 +1377,7 @@ static int generation_impl(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32
         if (t1 && e.tree1_len <= 0) return fail(c, "plan[%d]: missing second random tree", k);
         off[2 * k] = t0 ? e.tree0_off : -1; len[2 * k] = t0 ? e.tree0_len : 0;
         off[2 * k + 1] = t1 ? e.tree1_off : -1; len[2 * k + 1] = t1 ? e.tree1_len : 0;
-        c->hplan.p[k] = e;
+        hplan[k] = e;
     }
     auto t1 = now();
     if (programs) {
@@ -1367,34 +1389,34 @@ static int generation_impl(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32
         CU(c, c->hprog.reserve((size_t)n_instructions + 1));
         CU(c, c->ds[0].prog_pool.reserve((size_t)n_instructions + 1));
         for (int32_t t = 0; t < 2 * P; ++t) {
-            if (len[(size_t)t] <= 0) { c->hoff.p[t] = 0; c->hlen.p[t] = 0; continue; }
+            if (len[(size_t)t] <= 0) { hoff[t] = 0; hlen[t] = 0; continue; }
             if (!tree_pool || off[(size_t)t] < 0 || (int64_t)off[(size_t)t] + len[(size_t)t] > pool_len) return fail(c, "tree %d: tree exceeds the tree pool", t);
             const int32_t d = prog_desc_in[t], n = prog_desc_len(d), need = prog_desc_need(d), o = prog_off[t];
             if (n < 1 || o < 0 || (int64_t)o + n > n_instructions) return fail(c, "program of tree slot %d outside the program pool", t);
             if (need > kMaxStackLevels) return fail(c, "program of tree slot %d needs %d spill levels > %d", t, need, kMaxStackLevels);
             if (n > len[(size_t)t] / 4 + 1) return fail(c, "program of tree slot %d is longer than its tree", t);
-            for (int32_t i = 0; i < n; ++i) {
-                const uint32_t code = programs[2 * (size_t)(o + i)], ab = programs[2 * (size_t)(o + i) + 1];
-                const uint32_t level = code >> kLevelShift, aop = code & 7u;
-                if (aop > (uint32_t)A_MOV || (code & ~((~0u << kLevelShift) | K_LOADA | K_PUSH | K_POP | 7u)) ||
-                    (ab & 0xFFFFu) >= n_opd || (ab >> 16) >= n_opd || level >= (uint32_t)std::max(need, 1))
-                    return fail(c, "program of tree slot %d: bad instruction %d", t, i);
-            }
-            c->hoff.p[t] = o; c->hlen.p[t] = d;
+            // programs made by the library's own planner (gsgph_replay_generations) skip the per-instruction look
+            if (!trusted_programs)
+                for (int32_t i = 0; i < n; ++i) {
+                    const uint32_t code = programs[2 * (size_t)(o + i)], ab = programs[2 * (size_t)(o + i) + 1];
+                    const uint32_t level = code >> kLevelShift, aop = code & 7u;
+                    if (aop > (uint32_t)A_MOV || (code & ~((~0u << kLevelShift) | K_LOADA | K_PUSH | K_POP | 7u)) ||
+                        (ab & 0xFFFFu) >= n_opd || (ab >> 16) >= n_opd || level >= (uint32_t)std::max(need, 1))
+                        return fail(c, "program of tree slot %d: bad instruction %d", t, i);
+                }
+            hoff[t] = o; hlen[t] = d;
             max_need = std::max(max_need, need);
         }
         if (n_instructions > 0) memcpy(c->hprog.p, programs, sizeof(Ins) * (size_t)n_instructions);
         c->dcur = 0;
-        CU(c, cudaMemcpyAsync(c->dplan, c->hplan.p, sizeof(gsgp_plan_entry) * P, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->dpack, c->hpack.p, c->pack_bytes, cudaMemcpyHostToDevice, c->stream));   // plan | offsets | descriptors
         if (n_instructions > 0)
             CU(c, cudaMemcpyAsync(c->ds[0].prog_pool.p, c->hprog.p, sizeof(Ins) * (size_t)n_instructions, cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(c->dprog_off, c->hoff.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(c->ds[0].prog_desc, c->hlen.p, sizeof(int32_t) * 2 * P, cudaMemcpyHostToDevice, c->stream));
         if (c->fused) {
             const double n_cases = (double)(c->L.n_tr + c->L.n_te);
-            if (launch_gen(c, 0, P, 0, c->dsem[c->cur], c->dsem[c->cur ^ 1], gen_bytes(c->hplan.p, 0, P, n_cases))) return 1;
+            if (launch_gen(c, 0, P, 0, c->dsem[c->cur], c->dsem[c->cur ^ 1], gen_bytes(hplan, 0, P, n_cases))) return 1;
             if (finish_generation(c)) return 1;
-        } else if (run_generation_kernels(c, c->hplan.p, max_need)) return 1;
+        } else if (run_generation_kernels(c, hplan, max_need)) return 1;
         c->last_plan.assign(plan, plan + P);
         c->last_pool.assign(tree_pool, tree_pool + std::max(pool_len, 0));
         auto t2 = now();
@@ -1493,6 +1515,18 @@ int gsgp_generation_compiled(gsgp_ctx *c, const gsgp_plan_entry *plan, const int
     if (check_ready(c)) return 1;
     if (!programs) return fail(c, "null programs");
     return generation_impl(c, plan, tree_pool, pool_len, programs, n_instructions, prog_off, prog_desc, fit_out, fit_test_out, index_best_out);
+}
+
+// gsgp_generation_compiled for programs the library compiled itself (gsgph_replay_generations: the pipelined planner's
+// output): slot ranges and sizes are still checked, the 7 000 instructions of a generation are not re-read one by one.
+// Not part of the public ABI (include/gsgp_b200.h): a caller's own programs go through gsgp_generation_compiled.
+extern "C" int gsgp_internal_generation_trusted(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                                                const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off,
+                                                const int32_t *prog_desc, double *fit_out, double *fit_test_out, int32_t *index_best_out)
+{
+    if (check_ready(c)) return 1;
+    if (!programs) return fail(c, "null programs");
+    return generation_impl(c, plan, tree_pool, pool_len, programs, n_instructions, prog_off, prog_desc, fit_out, fit_test_out, index_best_out, true);
 }
 
 int gsgp_run_generations(gsgp_ctx *c, int32_t n)

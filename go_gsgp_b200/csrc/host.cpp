@@ -840,24 +840,41 @@ int gsgph_compile_plan(const gsgp_plan_entry *plan, int32_t population_size, con
     return 0;
 }
 
+// gsgp_b200.cu: gsgp_generation_compiled without the per-instruction check, for programs this library compiled itself
+extern "C" int gsgp_internal_generation_trusted(gsgp_ctx *c, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                                                const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off,
+                                                const int32_t *prog_desc, double *fit_out, double *fit_test_out, int32_t *index_best_out);
+
 int gsgph_replay_generations(gsgph_planner *pl, gsgp_ctx *ctx, int32_t n_generations, double *fit, double *fit_test,
                              int32_t *index_best, double *best_fit_history, double *best_fit_test_history)
 {
     if (!pl || !ctx || !fit || !fit_test || !index_best || n_generations < 0) return 1;
+    static const bool trace = getenv("GSGP_TRACE") != nullptr;
+    double us_plan = 0, us_prefetch = 0, us_call = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     for (int32_t g = 0; g < n_generations; ++g) {
         const gsgp_plan_entry *plan; const int32_t *pool; int32_t pool_len;
+        const auto t0 = now();
         if (int rc = gsgph_planner_plan(pl, fit, *index_best, &plan, &pool, &pool_len)) return rc;
+        const auto t1 = now();
         gsgph_planner_prefetch(pl, *index_best);                                // the next generation's draws start now
+        const auto t2 = now();
         int rc;
         if (pl->programs) {
             const gsgph_planner::Buf &B = pl->buf[pl->out];
-            rc = gsgp_generation_compiled(ctx, plan, pool, pool_len, reinterpret_cast<const uint32_t *>(B.prog.data()), B.n_ins,
-                                          B.prog_off.data(), B.prog_desc.data(), fit, fit_test, index_best);
+            // the planner's own programs: no per-instruction re-validation (gsgp_b200.cu)
+            rc = gsgp_internal_generation_trusted(ctx, plan, pool, pool_len, reinterpret_cast<const uint32_t *>(B.prog.data()), B.n_ins,
+                                                  B.prog_off.data(), B.prog_desc.data(), fit, fit_test, index_best);
         } else rc = gsgp_generation(ctx, plan, pool, pool_len, fit, fit_test, index_best);
         if (rc) return 4;                                                       // gsgp_last_error(ctx) says why
         if (best_fit_history) best_fit_history[g] = fit[*index_best];           // :1495-1496
         if (best_fit_test_history) best_fit_test_history[g] = fit_test[*index_best];
+        us_plan += us(t0, t1); us_prefetch += us(t1, t2); us_call += us(t2, now());
     }
+    if (trace && n_generations > 0)
+        fprintf(stderr, "gsgph_replay_generations: per generation plan %.1f us, prefetch %.1f us, generation call %.1f us\n",
+                us_plan / n_generations, us_prefetch / n_generations, us_call / n_generations);
     return 0;
 }
 

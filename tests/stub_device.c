@@ -73,6 +73,13 @@ int gsgp_generation_compiled(gsgp_ctx *ctx, const gsgp_plan_entry *plan, const i
     stub_fill(c, fit_out, fit_test_out, index_best_out);
     return 0;
 }
+/* the library's own replay loop (gsgph_replay_generations) hands its planner's programs to this internal twin */
+int gsgp_internal_generation_trusted(gsgp_ctx *ctx, const gsgp_plan_entry *plan, const int32_t *tree_pool, int32_t pool_len,
+                                     const uint32_t *programs, int32_t n_instructions, const int32_t *prog_off,
+                                     const int32_t *prog_desc, double *fit_out, double *fit_test_out, int32_t *index_best_out)
+{
+    return gsgp_generation_compiled(ctx, plan, tree_pool, pool_len, programs, n_instructions, prog_off, prog_desc, fit_out, fit_test_out, index_best_out);
+}
 int gsgp_get_semantic(gsgp_ctx *ctx, int32_t ind, double *out)
 {
     stub_ctx *c = (stub_ctx *)ctx;
