@@ -215,7 +215,9 @@ struct gsgp_ctx {
     double *dpartial = nullptr, *dsums = nullptr, *dsums_all = nullptr;
     unsigned char *dpack = nullptr; size_t pack_bytes = 0;        // one allocation: dplan | dprog_off | ds[0].prog_desc
     PinnedBuf<unsigned char> hpack;                               // its pinned image (gsgp_generation_compiled)
-    gsgp_plan_entry *dplan = nullptr;
+    gsgp_plan_entry *dplan = nullptr;                             // the plan of the generation being (or last) computed
+    gsgp_plan_entry *dplan_buf[2] = {nullptr, nullptr};           // device mode: generation g's plan lives in buffer g & 1
+    int32_t preselected = -1;                                     // generation whose selection rode in the previous finalize launch
     // random trees + programs of a generation.  Host replay uses set 0; device mode rotates through three sets:
     // generation g is consumed from set g%3 while plan_draw_kernel fills the sets of g+1 and g+2 on the second
     // stream (and the set of g stays readable for gsgp_get_tree until the draws of g+3).
@@ -614,6 +616,8 @@ int launch_ls_pass(gsgp_ctx *c, int mode, const double *sem, const double *osum_
 // the generation kernels left (gsop: 2048-case tiles, gen_kernel: 256-case tiles)
 int ensure_hist(gsgp_ctx *c, int32_t gen);
 
+PlanArgs plan_args(gsgp_ctx *c, int32_t generation);
+
 // best_gen >= 0: best_individual of the new fitness rides in the same launch (history slot best_gen)
 int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_tiles, int32_t best_gen = -1)
 {
@@ -639,8 +643,22 @@ int launch_finalize(gsgp_ctx *c, int mode, int old_buf, int new_buf, int32_t n_t
                       c->dfit_test[new_buf], P, c->cfg.world_size, mode, c->cfg.error_measure,
                       c->cfg.nrow, c->cfg.nrow_test};
         if (best_gen >= 0 && ensure_hist(c, best_gen)) return 1;
+        // device mode: the next generation's selection rides in the same launch (its draws run generations ahead)
+        static const bool no_fold = getenv("GSGP_NO_FOLDED_FINALIZE") != nullptr;
+        const int32_t next_gen = best_gen + 1;
+        const bool fold = !no_fold && best_gen >= 1 && mode == GS_MODE_GENERATION && c->cfg.rng_mode == GSGP_RNG_DEVICE_PHILOX &&
+                          c->drawn[next_gen % kDrawSets] == next_gen;
+        PlanArgs next{};
+        if (fold) {
+            next = plan_args(c, next_gen);
+            next.fit = c->dfit[new_buf];
+            CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[next_gen % kDrawSets], 0));
+        }
         ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
-        if (best_gen >= 0)
+        if (fold) {
+            finalize_select_kernel<<<1, 1024, 0, c->stream>>>(ReduceArgs{}, f, c->cfg.minimization_problem, c->dindex_best, c->dhist + best_gen, next, 0, 1);
+            c->preselected = next_gen;
+        } else if (best_gen >= 0)
             fitness_best_kernel<<<1, 1024, 0, c->stream>>>(f, c->cfg.minimization_problem, c->dindex_best, c->dhist + best_gen);
         else fitness_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(f);
         CU(c, cudaGetLastError());
@@ -700,10 +718,45 @@ int launch_best(gsgp_ctx *c, int buf, int32_t gen, bool best_done = false)
 }
 
 // after the generation kernels: fitness from the partials, update_tables, best_individual
+PlanArgs plan_args(gsgp_ctx *c, int32_t generation);
+
+// Small shapes on one GPU: the reduction, fitness + best individual AND (device mode) the next generation's selection in
+// one single-block launch (finalize_select_kernel) -- the generation's chain of dependent launches is two kernels long
+// instead of four.  Needs the next generation's draws (they run several generations ahead on their own streams).
+bool small_shape(const gsgp_ctx *c, int32_t n_tiles)
+{
+    static const bool off = getenv("GSGP_NO_FOLDED_FINALIZE") != nullptr;
+    return !off && c->cfg.world_size == 1 && !c->linsc && !c->keep_run &&
+           c->cfg.population_size <= 4096 && (int64_t)c->cfg.population_size * n_tiles <= (1 << 16);
+}
+
+int launch_finalize_select(gsgp_ctx *c, int old_buf, int new_buf, int32_t n_tiles, int32_t gen)
+{
+    const int P = c->cfg.population_size;
+    if (ensure_hist(c, gen)) return 1;
+    ReduceArgs r{c->dplan, c->dpartial, c->dsums, P, n_tiles, GS_MODE_GENERATION, XchgDev{}};
+    FitnessArgs f{c->dplan, c->dsums, c->dfit[old_buf], c->dfit_test[old_buf], c->dfit[new_buf], c->dfit_test[new_buf],
+                  P, 1, GS_MODE_GENERATION, c->cfg.error_measure, c->cfg.nrow, c->cfg.nrow_test};
+    const int32_t next_gen = gen + 1;
+    // host replay has no draws on the device (the plan comes with the next call): reduction + fitness + best only
+    const bool drawn = c->cfg.rng_mode == GSGP_RNG_DEVICE_PHILOX && c->drawn[next_gen % kDrawSets] == next_gen;
+    PlanArgs next{};
+    if (drawn) { next = plan_args(c, next_gen); next.fit = c->dfit[new_buf]; }   // the fitness this launch is about to write
+    if (drawn) CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[next_gen % kDrawSets], 0));
+    ProfScope ps(c, GSGP_K_FINALIZE, 0.0);
+    finalize_select_kernel<<<1, 1024, 0, c->stream>>>(r, f, c->cfg.minimization_problem, c->dindex_best, c->dhist + gen, next, 1, drawn ? 1 : 0);
+    CU(c, cudaGetLastError());
+    c->preselected = drawn ? next_gen : -1;
+    return 0;
+}
+
 int finish_generation(gsgp_ctx *c)
 {
     const int old_buf = c->cur, new_buf = c->cur ^ 1;
-    if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, c->fused ? c->n_tiles_gen : c->n_tiles, c->generation + 1)) return 1;
+    const int32_t n_tiles = c->fused ? c->n_tiles_gen : c->n_tiles;
+    if (small_shape(c, n_tiles)) {
+        if (launch_finalize_select(c, old_buf, new_buf, n_tiles, c->generation + 1)) return 1;
+    } else if (launch_finalize(c, GS_MODE_GENERATION, old_buf, new_buf, n_tiles, c->generation + 1)) return 1;
     c->cur = new_buf;                                                  // update_tables main_cpu.go:1191-1197
     c->generation++;
     if (launch_best(c, c->cur, c->generation, true)) return 1;         // :1492 (best_individual rode in the fitness launch)
@@ -760,7 +813,7 @@ PlanArgs plan_args(gsgp_ctx *c, int32_t generation)
 {
     gsgp_ctx::DrawSet &d = c->ds[generation % kDrawSets];
     PlanArgs a{};
-    a.plan = c->dplan; a.rec = d.rec; a.cand = d.cand; a.tree_pool = d.tree_pool; a.post_pool = c->dpost_pool;
+    a.plan = c->dplan_buf[generation & 1]; a.rec = d.rec; a.cand = d.cand; a.tree_pool = d.tree_pool; a.post_pool = c->dpost_pool;
     a.compile_scratch = c->dcompile_scratch; a.prog_pool = d.prog_pool.p; a.prog_desc = d.prog_desc;
     a.post_stride = c->post_stride;
     a.fit = c->dfit[c->cur]; a.index_best = c->dindex_best;
@@ -802,8 +855,11 @@ int launch_draw(gsgp_ctx *c, int32_t generation)
 int launch_select(gsgp_ctx *c, int32_t generation)
 {
     const PlanArgs a = plan_args(c, generation);
-    CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[generation % kDrawSets], 0));
     c->dcur = generation % kDrawSets;
+    c->dplan = a.plan;
+    if (c->preselected == generation) { c->preselected = -1; return 0; }    // chosen by the previous generation's finalize launch
+    c->preselected = -1;
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_draw[generation % kDrawSets], 0));
     ProfScope ps(c, GSGP_K_PLAN, 0.0);
     plan_select_kernel<<<(a.P + 255) / 256, 256, 0, c->stream>>>(a);
     CU(c, cudaGetLastError());
@@ -1005,6 +1061,11 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
     CUC(cudaMalloc((void **)&c->dpack, c->pack_bytes));
     CUC(cudaMemsetAsync(c->dpack, 0, c->pack_bytes, c->stream));
     c->dplan = reinterpret_cast<gsgp_plan_entry *>(c->dpack);
+    c->dplan_buf[0] = c->dplan; c->dplan_buf[1] = c->dplan;
+    if (cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX) {
+        CUC(cudaMalloc((void **)&c->dplan_buf[1], sizeof(gsgp_plan_entry) * P));
+        CUC(cudaMemsetAsync(c->dplan_buf[1], 0, sizeof(gsgp_plan_entry) * P, c->stream));
+    }
     c->dprog_off = reinterpret_cast<int32_t *>(c->dpack + sizeof(gsgp_plan_entry) * (size_t)P);
     c->ds[0].prog_desc = c->dprog_off + 2 * (size_t)P;
     const int n_sets = cfg->rng_mode == GSGP_RNG_DEVICE_PHILOX ? kDrawSets : 1;
@@ -1107,6 +1168,7 @@ void gsgp_destroy(gsgp_ctx *c)
     }
     for (int i = 0; i < kDrawSets; ++i) if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     for (int i = 0; i < kDrawStreams; ++i) if (c->draw_stream[i]) cudaStreamDestroy(c->draw_stream[i]);
+    if (c->dplan_buf[1] != c->dplan_buf[0]) cudaFree(c->dplan_buf[1]);
     cudaFree(c->dpack);                                               // dplan | dprog_off | ds[0].prog_desc
     cudaFree(c->dpost_pool); cudaFree(c->dcompile_scratch); cudaFree(c->dindex_best); cudaFree(c->dhist);
     for (double *p : c->run_sem) cudaFree(p);
@@ -1663,6 +1725,7 @@ int gsgp_set_fitness(gsgp_ctx *c, const double *fit, const double *fit_test)
 {
     if (check_ready(c)) return 1;
     const int P = c->cfg.population_size;
+    c->preselected = -1;                                               // a selection made on the old values is void
     if (fit) CU(c, cudaMemcpyAsync(c->dfit[c->cur], fit, sizeof(double) * P, cudaMemcpyHostToDevice, c->stream));
     if (fit_test) CU(c, cudaMemcpyAsync(c->dfit_test[c->cur], fit_test, sizeof(double) * P, cudaMemcpyHostToDevice, c->stream));
     if (launch_best(c, c->cur, c->generation)) return 1;
@@ -1676,6 +1739,7 @@ int gsgp_draw_plan(gsgp_ctx *c, int32_t generation, gsgp_plan_entry *plan_out)
     if (check_ready(c)) return 1;
     if (c->cfg.rng_mode != GSGP_RNG_DEVICE_PHILOX) return fail(c, "gsgp_draw_plan needs rng_mode = GSGP_RNG_DEVICE_PHILOX");
     for (int i = 0; i < kDrawStreams; ++i) CU(c, cudaStreamSynchronize(c->draw_stream[i]));   // pre-drawn generations are discarded
+    c->preselected = -1;
     CU(c, cudaEventRecord(c->ev_free[generation % kDrawSets], c->stream));
     if (launch_draw(c, generation)) return 1;
     if (launch_select(c, generation)) return 1;
