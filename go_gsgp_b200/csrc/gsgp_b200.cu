@@ -208,6 +208,7 @@ struct gsgp_ctx {
     // cases whose old values every individual has already consumed.  Memory = (1 + shift/n_pad) x the store, no copies.
     bool single_store = false;
     int32_t gen_warps = 16;                         // warps per gen_kernel block
+    int32_t gen_waves = 8;                          // blocks per SM a launch aims for (GSGP_GEN_WAVES)
     int32_t shift_tiles = 0;                                  // case tiles (256 cases) per block
     int64_t pitch = 0;                                        // row pitch of the store in doubles
     double *dfit[2] = {nullptr, nullptr}, *dfit_test[2] = {nullptr, nullptr};
@@ -400,7 +401,7 @@ size_t gen_smem_bytes(const gsgp_ctx *c, int32_t levels, int32_t ipg, int32_t wa
 }
 
 // the instantiated block sizes of gen_kernel (warps per block, one block per SM)
-#define GSGP_GEN_WARPS(X) X(24) X(20) X(16) X(12)
+#define GSGP_GEN_WARPS(X) X(28) X(24) X(20) X(16) X(12)
 
 template <int MEASURE>
 int launch_gen_kernel(gsgp_ctx *c, dim3 grid, size_t smem, const GenArgs &a)
@@ -426,14 +427,19 @@ int launch_gen_tiles(gsgp_ctx *c, int32_t k0, int32_t nk, int32_t slot_k0, const
 {
     if (nk <= 0 || tile_count <= 0) return 0;
     const int32_t n_blocks = tile_count;
-    static const int32_t waves = getenv("GSGP_GEN_WAVES") ? std::max(1, atoi(getenv("GSGP_GEN_WAVES"))) : 8;
+    const int32_t waves = c->gen_waves;
     const int32_t target = c->sm_count * waves;
     int32_t groups = std::max(1, (target + n_blocks - 1) / n_blocks);
-    groups = std::min(groups, std::max(1, (nk + c->gen_warps - 1) / c->gen_warps));   // >= one individual per warp
+    const int32_t groups_max = std::max(1, (nk + c->gen_warps - 1) / c->gen_warps);   // >= one individual per warp
+    groups = std::min(groups, groups_max);
+    // (The group count is not tuned to the launch's last "round" of blocks: 391 tiles x 3 groups fill 7.93 rounds of 148
+    // SMs and x 4 groups 10.57, yet 4 groups are faster, 0.593 against 0.628 ms -- blocks end at different times, and
+    // fewer, longer blocks lengthen the launch's tail.)
     int32_t ipg = (nk + groups - 1) / groups;
     while (ipg > 32 && gen_smem_bytes(c, c->gen_levels, ipg, c->gen_warps) > (size_t)227 * 1024) ipg = (ipg + 1) / 2;
     groups = (nk + ipg - 1) / ipg;
     if (groups > 65535) return fail(c, "population chunk too large for one launch");
+    if (c->gen_levels < 2) return fail(c, "gen_kernel needs two spill levels (sigma(R2) of a mutation waits in the last one)");
     GenArgs a{};
     a.plan = c->dplan; a.prog_pool = c->ds[c->dcur].prog_pool.p; a.prog_off = c->dprog_off; a.prog_desc = c->ds[c->dcur].prog_desc;
     a.slot_k0 = slot_k0; a.X = c->dX; a.y = c->dy; a.sym_val = c->dsym; a.nvar = c->cfg.nvar; a.nconst = c->cfg.num_constants;
@@ -996,14 +1002,12 @@ int gsgp_create(const gsgp_config *cfg, gsgp_ctx **out)
         const char *pl = getenv("GSGP_PIPELINE");
         c->gen_levels = 2;
         // warps per gen_kernel block (one block per SM): the kernel is bound by its warps' issue rate, so as many as the
-        // register file carries without spills; fewer when the dataset's columns leave less shared memory.
-        // GSGP_GEN_WARPS picks one of the instantiated sizes (A/B runs).
-        // warps per gen_kernel block (one block per SM): the kernel is bound by its warps' issue rate, so as many as the
-        // register file carries (24 x 80 registers); fewer when the dataset's columns leave less shared memory.
-        // GSGP_GEN_WARPS picks one of the instantiated sizes (A/B runs).
+        // register file carries without spills (28 x 72 registers); fewer when the dataset's columns leave less shared
+        // memory.  GSGP_GEN_WARPS picks one of the instantiated sizes (A/B runs).
         bool fits = false;
         const int env_w = getenv("GSGP_GEN_WARPS") ? atoi(getenv("GSGP_GEN_WARPS")) : 0;
-        for (int w : {env_w, 24, 20, 16, 12}) {
+        if (const char *e = getenv("GSGP_GEN_WAVES")) c->gen_waves = std::max(1, atoi(e));
+        for (int w : {env_w, 28, 24, 20, 16, 12}) {
             if (w <= 0) continue;
             c->gen_warps = w;
             fits = gen_smem_bytes(c, c->gen_levels, 32, c->gen_warps) <= (size_t)kMaxSmem;

@@ -207,6 +207,46 @@ def test_fused_path_runs_long_programs_in_chunks(depth, full):
     e.close(); o.close()
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_mutation_with_every_combination_of_spill_needs(ragged):
+    """gen_kernel keeps sigma(R2) of a mutation in the warp's last spill level while tree 1 is interpreted.  A full binary
+    tree of depth d needs d - 1 spill levels and the kernel keeps two in shared memory, so the pairs below cover: both
+    trees need every level (sigma(R2) waits in the child's own tile in global memory), only tree 1 does (the two trees
+    swap places and ms changes sign), only tree 2 does, a tree on the local-memory stack on either side, and shallow
+    trees -- each against the oracle, inside full tiles and (ragged) in a tile cut by the train | test boundary."""
+    g = _engine_mod()
+    rng = np.random.default_rng(2024)
+    V, P = 6, 18
+    N, nrow = (1500, 1100) if ragged else (1024, 768)
+    X, y, _ = synth_dataset(3, N, V)
+    depths = [(3, 3), (3, 2), (2, 3), (3, 1), (1, 3), (4, 3), (3, 4), (4, 4), (2, 2), (1, 1), (3, 3), (3, 2), (5, 3), (3, 5), (2, 1), (1, 2), (3, 3), (2, 3)]
+    trees = []
+    for d0, d1 in depths:
+        trees += [_random_tree_array(rng, d0, V, True), _random_tree_array(rng, d1, V, True)]
+    off = np.cumsum([0] + [len(t) for t in trees])
+    pool = np.concatenate(trees).astype(np.int32)
+    cfg = ob.make_config(population_size=P, error_measure=ob.MSE)
+    o = ob.Oracle(cfg, X, y, nrow)
+    o.create_T_F()
+    e = g.Engine(population_size=P, nvar=V, nrow=nrow, nrow_test=N - nrow, error_measure=ob.MSE)
+    e.set_dataset(X, y); e.set_constants(o.symbol_values())
+    for i in range(P):
+        sem = rng.normal(size=N)
+        o.seed_semantic(i, sem); e.seed_semantic(i, sem)
+    o.initialize_population(P); o.evaluate(); e.fitness_all()
+    plan = np.zeros(P, ob.PLAN_DTYPE)
+    for k in range(P):
+        t0, t1 = 2 * k, 2 * k + 1
+        plan[k] = (ob.OP_MUT, 0, (k + 5) % P, 0, off[t0], len(trees[t0]), off[t1], len(trees[t1]), float(rng.uniform(-1, 1)))
+    for gen in range(2):                                               # the second generation reads what the first one wrote
+        o.generation_replay(plan, pool)
+        fit, fit_test, best = e.generation(plan, pool)
+        assert_close(e.get_semantics(), o.semantics(), TOL, f"gen {gen}: children", atol=1e-14)
+        assert_close(fit, o.fit(), TOL, "fit"); assert_close(fit_test, o.fit_test(), TOL, "fit_test")
+        assert same_best(best, o)
+    e.close(); o.close()
+
+
 @pytest.mark.parametrize("measure", [ob.MSE, ob.RMSE, ob.MAE, ob.MRE])
 def test_initial_evaluate(measure):
     X, y, nrow = synth_dataset(1, 1250, 5, nrow=1000)

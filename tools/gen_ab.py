@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B timing of the fused generation kernel's block sizes (GSGP_GEN_WARPS) in one process.
+"""A/B timing of the fused generation kernel's variants (GSGP_GEN_WARPS / GSGP_GEN_WAVES) in one process.
 
     python tools/gen_ab.py [--workload cfg2] [--steps 30] [--variants 16,20,24] [--pop N]
 
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--variants", default="16,20,24,28")
+    ap.add_argument("--variants", default="20,24,28")
     ap.add_argument("--pop", type=int, default=0)
     ap.add_argument("--cases", type=int, default=0)
     args = ap.parse_args()
@@ -51,7 +51,13 @@ def main():
     init_trees = host.initialize_population(0)
     ref_fit = None
     for var in args.variants.split(","):
-        os.environ["GSGP_GEN_WARPS"] = var
+        # a variant is warps[:waves], e.g. 28, 24, 28:12
+        parts = var.split(":")
+        os.environ["GSGP_GEN_WARPS"] = parts[0]
+        if len(parts) > 1 and parts[1]:
+            os.environ["GSGP_GEN_WAVES"] = parts[1]
+        else:
+            os.environ.pop("GSGP_GEN_WAVES", None)
         os.environ["GSGP_PIPELINE"] = "fused"
         e = Engine(rng_mode=capi.RNG_DEVICE_PHILOX, population_size=P, nvar=V, nrow=nrow, nrow_test=n - nrow,
                    max_depth_creation=w["depth"], error_measure=capi.RMSE, p_crossover=w["p_xo"], p_mutation=w["p_mut"],
