@@ -473,7 +473,7 @@ def main():
     achieved_8d = local_updates * bpu_8d * K / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured in this run -- the figure of the committed
     # `ncu --set full` capture of the same workload and kernel (profiles/README.md), null where there is none
-    traffic_tab = {("cfg2", True): (1.881e9, "profiles/r02c_gen_kernel_cfg2_ncu_summary.csv"),
+    traffic_tab = {("cfg2", True): (1.888e9, "profiles/r02e_gen_kernel_cfg2_ncu_summary.csv"),
                    ("cfg2", False): (2.895e9, "profiles/r01_gsop_kernel_final_ncu_summary.csv")}
     traffic, traffic_src = traffic_tab.get((args.workload, fused), (None, None)) if world == 1 else (None, None)
     n_gu, ms_gu, _ = prof_u[capi.K_GSOP]
@@ -497,8 +497,8 @@ def main():
                 "launches": n_gs, "ms_total": ms_gs, "ms_per_launch": ms_gs / max(1, n_gs), "pipeline": "fused" if fused else "unfused",
                 "interp_kernel": {"launches": n_it, "ms_total": ms_it},
                 "share_of_step": {"gs": ms_gs / ms_dev if ms_dev else None, "interp": ms_it / ms_dev if ms_dev else None},
-                "limiter": ("instruction issue at 7 warps per scheduler (ncu, profiles/r02c_gen_kernel_cfg2_ncu_summary.csv): issue slots 61 %, "
-                            "l1tex data pipe 72 % (shared-memory operand fetches of the interpreter), fp64 pipe 49 %, DRAM 38 %; "
+                "limiter": ("instruction issue at 7 warps per scheduler (ncu, profiles/r02e_gen_kernel_cfg2_ncu_summary.csv): issue slots 63 %, "
+                            "l1tex data pipe 74 % (shared-memory operand fetches of the interpreter), fp64 pipe 49 %, DRAM 39 %; "
                             "see gs_kernel_unfused for the HBM-bound GS kernel") if fused else "HBM",
                 "gs_kernel_unfused": gs_unfused}
 
