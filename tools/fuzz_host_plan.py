@@ -1,7 +1,7 @@
 """Differential fuzz of the two restatements of main_cpu.go's RNG-order-defining half: the product's host driver
 (gsgph_*: serial plan builder and pipelined planner) against the oracle, under Go's rand.Seed stream, on random
 configurations (population, depth, constants, tournament size, init type, operator rates, seeded individuals, seeds
-incl. negative).  Runs for about 150 s.  Last run: 38 118 configurations, 0 differences.
+incl. negative).  Runs for about 150 s.  Last run (end of round 2): 43 014 configurations, 0 differences.
     python tools/fuzz_host_plan.py"""
 import sys, time
 import os
